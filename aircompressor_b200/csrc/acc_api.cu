@@ -1,0 +1,353 @@
+// acc_api.cu -- host runtime and C ABI of libaircompress_cuda.so (see include/aircompress_cuda.h).
+//
+// There is deliberately no CPU code path for any codec in this file: every compress / decompress /
+// hash request becomes a kernel launch, and when no GPU is usable acc_init() fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "acc_device.cuh"
+
+struct acc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    unsigned int *counters = nullptr;   // ring of work-stealing counters
+    int counter_next = 0;
+    static constexpr int kCounters = 256;
+    // grow-only staging for the host-pointer entry points
+    uint8_t *d_src = nullptr; int64_t d_src_cap = 0;
+    uint8_t *d_dst = nullptr; int64_t d_dst_cap = 0;
+    int64_t *d_idx = nullptr; int64_t d_idx_cap = 0;   // src_off | src_len | dst_off | dst_cap | out_len, then status
+    void *d_scratch = nullptr; int64_t d_scratch_cap = 0;
+    int64_t *h_idx = nullptr; int64_t h_idx_cap = 0;   // pinned mirror of d_idx
+    int32_t last_status = 0;
+    int64_t last_offset = 0;
+    int64_t launches = 0;
+    int tuning_ctas_per_sm = 0;
+};
+
+static thread_local int32_t t_init_error = 0;
+static const char *zstd_reason_text(int32_t reason);   // zstd_host.inc
+static int64_t zstd_scratch_bytes(int32_t op, int64_t n);
+
+#define CU_TRY(expr, fail_stmt) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail_stmt; } } while (0)
+
+extern "C" {
+
+int32_t acc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t acc_init_error(void) { return t_init_error; }
+
+acc_ctx *acc_init(int32_t device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        t_init_error = ACC_STATUS(ACC_E_CUDA, (int) (e != cudaSuccess ? e : cudaErrorInvalidDevice));
+        return nullptr;
+    }
+    acc_ctx *c = new acc_ctx();
+    c->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->counters, sizeof(unsigned int) * acc_ctx::kCounters) == cudaSuccess;
+    if (!ok) {
+        t_init_error = ACC_STATUS(ACC_E_CUDA, (int) cudaGetLastError());
+        delete c;
+        return nullptr;
+    }
+    t_init_error = 0;
+    return c;
+}
+
+void acc_destroy(acc_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    cudaFree(c->counters); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_idx); cudaFree(c->d_scratch);
+    if (c->h_idx) cudaFreeHost(c->h_idx);
+    delete c;
+}
+
+void *acc_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, (size_t) (bytes > 0 ? bytes : 1)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void acc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int32_t acc_last_error(acc_ctx *c, int64_t *offset)
+{
+    if (!c) return ACC_STATUS(ACC_E_ARGUMENT, 0);
+    if (offset) *offset = c->last_offset;
+    return c->last_status;
+}
+
+int32_t acc_sm_count(acc_ctx *c) { return c ? c->sm_count : 0; }
+int64_t acc_kernel_launches(acc_ctx *c) { return c ? c->launches : 0; }
+
+int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
+{
+    if (!c) return 0;
+    if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
+    return 0;
+}
+
+const char *acc_code_name(int32_t code)
+{
+    switch (code & 0xff) {
+        case ACC_OK: return "ok";
+        case ACC_E_MALFORMED: return "malformed input";
+        case ACC_E_DST_TOO_SMALL: return "output buffer too small";
+        case ACC_E_ARGUMENT: return "illegal argument";
+        case ACC_E_CUDA: return "cuda error";
+        case ACC_E_UNSUPPORTED: return "unsupported";
+        default: return "unknown";
+    }
+}
+
+const char *acc_reason_text(int32_t reason)
+{
+    switch (reason) {
+        case ACC_R_NONE: return "Malformed input";
+        case ACC_R_INPUT_EMPTY: return "input is empty";
+        case ACC_R_LAST_LITERAL_OUTSIDE: return "attempt to write last literal outside of destination buffer";
+        case ACC_R_ALL_INPUT_CONSUMED: return "all input must be consumed";
+        case ACC_R_OFFSET_OUTSIDE: return "offset outside destination buffer";
+        case ACC_R_LAST5_LITERALS: return "last 5 bytes must be literals";
+        case ACC_R_LZ4_ZERO_CAPACITY: return "zero-capacity output (reference returns -1)";
+        case ACC_R_SNAPPY_TRUNCATED: return "Input is truncated";
+        case ACC_R_SNAPPY_VARINT_HIGHBIT: return "last byte of compressed length int has high bit set";
+        case ACC_R_SNAPPY_NEG_LENGTH: return "invalid compressed length";
+        case ACC_R_SNAPPY_LEN_GT_CAP: return "Uncompressed length %s must be less than %s";
+        case ACC_R_SNAPPY_LEN_MISMATCH: return "Recorded length is %s bytes but actual length after decompression is %s bytes ";
+        case ACC_R_MAX_OUTPUT_TOO_SMALL: return "Max output length must be larger than maxCompressedLength";
+        case ACC_R_MAX_INPUT_EXCEEDED: return "Max input length exceeded";
+        default: break;
+    }
+    return zstd_reason_text(reason);
+}
+
+int64_t acc_lz4_compress_bound(int64_t n) { return n + n / 255 + 16; }          // Lz4RawCompressor.java:64-67
+int64_t acc_snappy_compress_bound(int64_t n) { return 32 + n + n / 6; }         // SnappyRawCompressor.java:47-70
+int64_t acc_zstd_compress_bound(int64_t n)                                       // ZstdJavaCompressor.java:31-40
+{
+    int64_t r = n + (n >> 8);
+    if (n < 128 * 1024) r += (128 * 1024 - n) >> 11;
+    return r;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+static unsigned int *next_counter(acc_ctx *c, cudaStream_t st)
+{
+    unsigned int *p = c->counters + c->counter_next;
+    c->counter_next = (c->counter_next + 1) % acc_ctx::kCounters;
+    cudaMemsetAsync(p, 0, sizeof(unsigned int), st);
+    return p;
+}
+
+
+static bool grow(void **p, int64_t *cap, int64_t need, bool host)
+{
+    if (need <= *cap) return true;
+    int64_t ncap = need + need / 4 + 4096;
+    if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t e = host ? cudaMallocHost(p, (size_t) ncap) : cudaMalloc(p, (size_t) ncap);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    *cap = ncap;
+    return true;
+}
+
+// enqueue one batch kernel; all pointers in b are device pointers
+static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint64_t seed)
+{
+    b.work_counter = next_counter(c, st);
+    switch (op) {
+        case ACC_OP_LZ4_COMPRESS: acc_launch_lz4_compress(b, c->sm_count, st); break;
+        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
+        case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
+        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
+        case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
+        case ACC_OP_ZSTD_COMPRESS:
+        case ACC_OP_ZSTD_DECOMPRESS: {
+            int64_t need = zstd_scratch_bytes(op, b.n);
+            if (!grow(&c->d_scratch, &c->d_scratch_cap, need, false)) return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
+            if (op == ACC_OP_ZSTD_COMPRESS) acc_launch_zstd_compress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);
+            else acc_launch_zstd_decompress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);
+            break;
+        }
+        default: return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+    }
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -ACC_STATUS(ACC_E_CUDA, (int) e);
+    return 0;
+}
+
+static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const int64_t *src_off, const int64_t *src_len,
+                          void *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int32_t *status,
+                          int64_t n, int32_t flags, int64_t stream, uint64_t seed)
+{
+    if (!c || n < 0 || op < 0 || op > ACC_OP_XXH64) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+    if (cudaSetDevice(c->device) != cudaSuccess) return -ACC_STATUS(ACC_E_CUDA, (int) cudaGetLastError());
+    cudaStream_t st = stream ? (cudaStream_t) (uintptr_t) stream : c->stream;
+    if (n == 0) return 0;
+
+    if (flags & ACC_F_DEVICE_POINTERS) {
+        AccBatch b{(const uint8_t *) src_base, src_off, src_len, (uint8_t *) dst_base, dst_off, dst_cap, out_len, status, n, nullptr};
+        return enqueue(c, op, b, st, seed);
+    }
+
+    // ---- host pointers: stage, run, copy back, synchronise ----
+    const bool has_dst = op != ACC_OP_XXH64;
+    int64_t src_lo = INT64_MAX, src_hi = 0, dst_lo = INT64_MAX, dst_hi = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (src_len[i] < 0 || src_off[i] < 0) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+        if (src_off[i] < src_lo) src_lo = src_off[i];
+        if (src_off[i] + src_len[i] > src_hi) src_hi = src_off[i] + src_len[i];
+        if (has_dst) {
+            if (dst_cap[i] < 0 || dst_off[i] < 0) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+            if (dst_off[i] < dst_lo) dst_lo = dst_off[i];
+            if (dst_off[i] + dst_cap[i] > dst_hi) dst_hi = dst_off[i] + dst_cap[i];
+        }
+    }
+    if (src_hi < src_lo) src_hi = src_lo;
+    if (!has_dst) { dst_lo = 0; dst_hi = 0; }
+    if (dst_hi < dst_lo) dst_hi = dst_lo;
+    const int64_t src_bytes = src_hi - src_lo, dst_bytes = dst_hi - dst_lo;
+    // keep the relative alignment of the caller's buffers (mod 16) so kernels see the same layout
+    const int64_t src_pad = src_lo & 15, dst_pad = dst_lo & 15;
+    const int64_t idx_words = 5 * n;                       // src_off, src_len, dst_off, dst_cap, out_len
+    const int64_t idx_bytes = idx_words * 8 + n * 4;       // + status
+    if (!grow((void **) &c->d_src, &c->d_src_cap, src_bytes + src_pad + 64, false) ||
+        !grow((void **) &c->d_dst, &c->d_dst_cap, dst_bytes + dst_pad + 64, false) ||
+        !grow((void **) &c->d_idx, &c->d_idx_cap, idx_bytes, false) ||
+        !grow((void **) &c->h_idx, &c->h_idx_cap, idx_bytes, true)) {
+        return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
+    }
+    int64_t *h = c->h_idx;
+    for (int64_t i = 0; i < n; i++) {
+        h[i] = src_off[i] - src_lo + src_pad;
+        h[n + i] = src_len[i];
+        h[2 * n + i] = has_dst ? dst_off[i] - dst_lo + dst_pad : 0;
+        h[3 * n + i] = has_dst ? dst_cap[i] : 0;
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_idx, h, (size_t) (4 * n * 8), cudaMemcpyHostToDevice, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+    if (src_bytes > 0)
+        CU_TRY(cudaMemcpyAsync(c->d_src + src_pad, (const uint8_t *) src_base + src_lo, (size_t) src_bytes, cudaMemcpyHostToDevice, st),
+               return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+    AccBatch b{c->d_src, c->d_idx, c->d_idx + n, c->d_dst, c->d_idx + 2 * n, c->d_idx + 3 * n, c->d_idx + 4 * n,
+               (int32_t *) (c->d_idx + 5 * n), n, nullptr};
+    int32_t r = enqueue(c, op, b, st, seed);
+    if (r != 0) return r;
+    CU_TRY(cudaMemcpyAsync(h + 4 * n, c->d_idx + 4 * n, (size_t) (n * 8 + n * 4), cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+    if (has_dst && dst_bytes > 0) {
+        if (op == ACC_OP_LZ4_DECOMPRESS || op == ACC_OP_SNAPPY_DECOMPRESS || op == ACC_OP_ZSTD_DECOMPRESS || n > 1) {
+            CU_TRY(cudaMemcpyAsync((uint8_t *) dst_base + dst_lo, c->d_dst + dst_pad, (size_t) dst_bytes, cudaMemcpyDeviceToHost, st),
+                   return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+    if (has_dst && dst_bytes > 0 && !(op == ACC_OP_LZ4_DECOMPRESS || op == ACC_OP_SNAPPY_DECOMPRESS || op == ACC_OP_ZSTD_DECOMPRESS || n > 1)) {
+        // single compress call: copy back only the bytes produced
+        int64_t produced = h[4 * n];
+        int32_t stt = ((int32_t *) (h + 5 * n))[0];
+        if (stt == 0 && produced > 0) {
+            CU_TRY(cudaMemcpy((uint8_t *) dst_base + dst_lo, c->d_dst + dst_pad, (size_t) produced, cudaMemcpyDeviceToHost),
+                   return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        }
+    }
+    memcpy(out_len, h + 4 * n, (size_t) (n * 8));
+    if (status) memcpy(status, h + 5 * n, (size_t) (n * 4));
+    return 0;
+}
+
+static int64_t single_impl(acc_ctx *c, int32_t op, const void *src, int64_t src_len, void *dst, int64_t dst_cap, uint64_t seed)
+{
+    if (!c) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+    if (src_len < 0 || dst_cap < 0) { c->last_status = ACC_STATUS(ACC_E_ARGUMENT, 0); c->last_offset = 0; return -c->last_status; }
+    int64_t zero = 0, out_len = 0;
+    int32_t status = 0;
+    int32_t r = batch_impl(c, op, src, &zero, &src_len, dst, &zero, &dst_cap, &out_len, &status, 1, 0, 0, seed);
+    if (r != 0) { c->last_status = -r; c->last_offset = 0; return r; }
+    if (status != 0) { c->last_status = status; c->last_offset = out_len; return -(int64_t) status; }
+    c->last_status = 0;
+    c->last_offset = 0;
+    return out_len;
+}
+
+extern "C" {
+
+int32_t acc_batch(acc_ctx *c, int32_t op, const void *src_base, const int64_t *src_off, const int64_t *src_len,
+                  void *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int32_t *status,
+                  int64_t n, int32_t flags, int64_t stream)
+{
+    return batch_impl(c, op, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status, n, flags, stream, 0);
+}
+
+#define ACC_BATCH_ALIAS(name, op)                                                                                          \
+    int32_t name(acc_ctx *c, const void *sb, const int64_t *so, const int64_t *sl, void *db, const int64_t *d_o,          \
+                 const int64_t *dc, int64_t *ol, int32_t *stt, int64_t n, int32_t flags, int64_t stream)                   \
+    { return batch_impl(c, op, sb, so, sl, db, d_o, dc, ol, stt, n, flags, stream, 0); }
+ACC_BATCH_ALIAS(acc_lz4_compress_batch, ACC_OP_LZ4_COMPRESS)
+ACC_BATCH_ALIAS(acc_lz4_decompress_batch, ACC_OP_LZ4_DECOMPRESS)
+ACC_BATCH_ALIAS(acc_snappy_compress_batch, ACC_OP_SNAPPY_COMPRESS)
+ACC_BATCH_ALIAS(acc_snappy_decompress_batch, ACC_OP_SNAPPY_DECOMPRESS)
+ACC_BATCH_ALIAS(acc_zstd_compress_batch, ACC_OP_ZSTD_COMPRESS)
+ACC_BATCH_ALIAS(acc_zstd_decompress_batch, ACC_OP_ZSTD_DECOMPRESS)
+
+int32_t acc_xxh64_batch(acc_ctx *c, const void *sb, const int64_t *so, const int64_t *sl, int64_t *hashes, int64_t n, int32_t flags, int64_t stream)
+{
+    return batch_impl(c, ACC_OP_XXH64, sb, so, sl, nullptr, nullptr, nullptr, hashes, nullptr, n, flags, stream, 0);
+}
+
+int64_t acc_lz4_compress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_LZ4_COMPRESS, s, sl, d, dc, 0); }
+int64_t acc_lz4_decompress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_LZ4_DECOMPRESS, s, sl, d, dc, 0); }
+int64_t acc_snappy_compress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_SNAPPY_COMPRESS, s, sl, d, dc, 0); }
+int64_t acc_snappy_decompress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_SNAPPY_DECOMPRESS, s, sl, d, dc, 0); }
+int64_t acc_zstd_compress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_ZSTD_COMPRESS, s, sl, d, dc, 0); }
+int64_t acc_zstd_decompress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_ZSTD_DECOMPRESS, s, sl, d, dc, 0); }
+
+int64_t acc_xxh64(acc_ctx *c, const void *src, int64_t len, int64_t seed)
+{
+    if (!c || len < 0) return 0;
+    int64_t zero = 0, h = 0;
+    int32_t r = batch_impl(c, ACC_OP_XXH64, src, &zero, &len, nullptr, nullptr, nullptr, &h, nullptr, 1, 0, 0, (uint64_t) seed);
+    c->last_status = r ? -r : 0;
+    return h;
+}
+
+// SnappyRawDecompressor.readUncompressedLength (snappy/SnappyRawDecompressor.java:277-321): header-only, host side.
+int64_t acc_snappy_uncompressed_length(const void *src, int64_t src_len, int64_t *err_offset)
+{
+    const uint8_t *in = (const uint8_t *) src;
+    uint32_t result = 0;
+    int64_t n = 0;
+    for (int shift = 0;; shift += 7) {
+        if (n >= src_len) { if (err_offset) *err_offset = src_len - n; return -(int64_t) ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_TRUNCATED); }
+        uint32_t b = in[n++];
+        result |= (b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        if (shift == 28) { if (err_offset) *err_offset = n; return -(int64_t) ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_VARINT_HIGHBIT); }
+    }
+    if ((int32_t) result < 0) { if (err_offset) *err_offset = 0; return -(int64_t) ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_NEG_LENGTH); }
+    return (int64_t) result;
+}
+
+}  // extern "C"
+
+#include "zstd_host.inc"

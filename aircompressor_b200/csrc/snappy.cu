@@ -1,0 +1,280 @@
+// snappy.cu -- Snappy raw-format decode / encode kernels for sm_100a.
+//
+// Replaces SnappyRawDecompressor.decompress / uncompressAll (snappy/SnappyRawDecompressor.java:35-220)
+// and SnappyRawCompressor.compress (snappy/SnappyRawCompressor.java:74-233).  Decode is bit-exact with
+// the Java decoder (same accept/reject decisions and error offsets); encode emits a valid stream the
+// Java decoder round-trips (AbstractTestCompression.java:362-393).
+#include "acc_device.cuh"
+
+namespace {
+
+// SnappyRawDecompressor.java:238-271 opLookupTable as a formula: bits 0-7 length, 8-10 offset/256,
+// 11-13 trailer bytes.
+__device__ __forceinline__ uint32_t snappy_op_entry(uint32_t op)
+{
+    uint32_t kind = op & 3, hi = op >> 2;
+    if (kind == 0) return hi < 60 ? hi + 1 : (((hi - 59) << 11) | 1);
+    if (kind == 1) return (1u << 11) | ((op >> 5) << 8) | (4 + (hi & 7));
+    if (kind == 2) return (2u << 11) | (hi + 1);
+    return (4u << 11) | (hi + 1);
+}
+
+// Java readUncompressedLength (SnappyRawDecompressor.java:277-321). Returns status word (0 = ok).
+__device__ __forceinline__ int32_t snappy_read_length(const uint8_t *in, int64_t in_len, uint32_t *result_out, int *bytes_read, int64_t *err_off)
+{
+    uint32_t result = 0;
+    int n = 0;
+    for (int shift = 0;; shift += 7) {
+        if (n >= in_len) { *err_off = in_len - n; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_TRUNCATED); }
+        uint32_t b = in[n++];
+        result |= (b & 0x7f) << shift;
+        if (!(b & 0x80)) break;
+        if (shift == 28) { *err_off = n; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_VARINT_HIGHBIT); }
+    }
+    if ((int32_t) result < 0) { *err_off = 0; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_NEG_LENGTH); }
+    *result_out = result;
+    *bytes_read = n;
+    return 0;
+}
+
+__device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ in0, int64_t in_len0, uint8_t *out, int64_t out_cap,
+                                                    int64_t *out_len, int32_t *status, int lane)
+{
+#define SN_FAIL(off) do { if (lane == 0) { *out_len = (off); *status = ACC_STATUS(ACC_E_MALFORMED, ACC_R_NONE); } return; } while (0)
+    uint32_t expected = 0;
+    int br = 0;
+    int64_t eoff = 0;
+    int32_t st = snappy_read_length(in0, in_len0, &expected, &br, &eoff);
+    if (st != 0) { if (lane == 0) { *out_len = eoff; *status = st; } return; }
+    if ((int64_t) expected > out_cap) {
+        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_SNAPPY_LEN_GT_CAP); }
+        return;
+    }
+    const uint8_t *in = in0 + br;
+    const int64_t in_len = in_len0 - br;
+    const int64_t fast_output_limit = out_cap - 8;
+    int64_t ip = 0, op = 0;
+
+    while (ip < in_len) {
+        const uint32_t opc = in[ip++];
+        const uint32_t entry = snappy_op_entry(opc);
+        const int trailer_bytes = (int) (entry >> 11);
+        if (!(ip + 4 < in_len)) {
+            if (ip + trailer_bytes > in_len) SN_FAIL(ip);
+        }
+        uint32_t trailer = 0;
+        for (int i = trailer_bytes - 1; i >= 0; i--) trailer = (trailer << 8) | in[ip + i];
+        if ((int32_t) trailer < 0) SN_FAIL(ip);
+        ip += trailer_bytes;
+        const uint32_t length = entry & 0xff;
+
+        if ((opc & 3) == 0) {
+            const uint32_t ll = length + trailer;
+            if ((int32_t) ll < 0) SN_FAIL(ip);
+            const int64_t lit_out_limit = op + (int64_t) ll;
+            if (lit_out_limit > fast_output_limit || ip + (int64_t) ll > in_len - 8) {
+                if (lit_out_limit > out_cap || ip + (int64_t) ll > in_len) SN_FAIL(ip);
+            }
+            warp_copy(out + op, in + ip, ll, lane);
+            ip += ll;
+            op = lit_out_limit;
+        }
+        else {
+            const uint32_t moff = (entry & 0x700) + trailer;
+            if ((int32_t) moff <= 0) SN_FAIL(ip);
+            if ((int64_t) moff > op || op + (int64_t) length > out_cap) SN_FAIL(ip);
+            __syncwarp();
+            warp_match_copy(out + op, moff, length, lane);
+            __syncwarp();
+            op += length;
+        }
+    }
+    if ((int64_t) expected != op) {
+        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_LEN_MISMATCH); }
+        return;
+    }
+    if (lane == 0) { *out_len = expected; *status = 0; }
+#undef SN_FAIL
+}
+
+__global__ void __launch_bounds__(256) snappy_decompress_kernel(AccBatch b)
+{
+    const int lane = lane_id();
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if ((int64_t) idx >= b.n) break;
+        snappy_decode_block(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
+                            b.out_len + idx, b.status + idx, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encode: one warp per input; independent 64 KiB fragments (SnappyRawCompressor.java:37-38,93) are
+// walked in order with a 16,384 x uint16 position table in shared memory (same shape as the
+// reference's short[16384], SnappyRawCompressor.java:43-45,348-361) that is reset per fragment.
+// 32 positions are probed per step with the reference's hash (value * 0x1e35a7bd >>> shift,
+// SnappyRawCompressor.java:368-371); ballot selects the first match, a second ballot extends it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSnTableBits = 14;
+constexpr int kSnTable = 1 << kSnTableBits;
+constexpr int kSnWarpsPerCta = 2;
+constexpr int kSnFragment = 1 << 16;
+
+__device__ __forceinline__ uint32_t snappy_hash(uint32_t v) { return (v * 0x1e35a7bdu) >> (32 - kSnTableBits); }
+
+__device__ __forceinline__ int64_t snappy_emit_literal(uint8_t *out, int64_t op, const uint8_t *lit, int64_t ll, int lane)
+{
+    // SnappyRawCompressor.java:268-298 emitLiteralLength
+    uint32_t n = (uint32_t) (ll - 1);
+    int hdr;
+    if (n < 60) { hdr = 1; if (lane == 0) out[op] = (uint8_t) (n << 2); }
+    else {
+        int bytes = n < (1u << 8) ? 1 : n < (1u << 16) ? 2 : n < (1u << 24) ? 3 : 4;
+        hdr = 1 + bytes;
+        if (lane == 0) out[op] = (uint8_t) ((59 + bytes) << 2);
+        if (lane >= 1 && lane <= bytes) out[op + lane] = (uint8_t) (n >> (8 * (lane - 1)));
+    }
+    op += hdr;
+    warp_copy(out + op, lit, ll, lane);
+    return op + ll;
+}
+
+__device__ __forceinline__ int64_t snappy_emit_copy(uint8_t *out, int64_t op, uint32_t offset, int64_t len, int lane)
+{
+    // SnappyRawCompressor.java:312-345 emitCopy: 64-byte COPY_2 chunks while len >= 68, one 60-byte
+    // chunk if len > 64, then COPY_1 (len 4..11, offset < 2048) or COPY_2.
+    int64_t n64 = len >= 68 ? (len - 68) / 64 + 1 : 0;
+    for (int64_t i = lane; i < n64; i += 32) {
+        uint8_t *o = out + op + i * 3;
+        o[0] = (uint8_t) (2 + ((64 - 1) << 2)); o[1] = (uint8_t) offset; o[2] = (uint8_t) (offset >> 8);
+    }
+    op += n64 * 3;
+    len -= n64 * 64;
+    if (lane == 0) {
+        if (len > 64) {
+            out[op] = (uint8_t) (2 + ((60 - 1) << 2)); out[op + 1] = (uint8_t) offset; out[op + 2] = (uint8_t) (offset >> 8);
+        }
+    }
+    if (len > 64) { op += 3; len -= 60; }
+    if (len < 12 && offset < 2048) {
+        if (lane == 0) {
+            out[op] = (uint8_t) (1 + ((len - 4) << 2) + ((offset >> 8) << 5));
+            out[op + 1] = (uint8_t) offset;
+        }
+        op += 2;
+    }
+    else {
+        if (lane == 0) {
+            out[op] = (uint8_t) (2 + ((len - 1) << 2)); out[op + 1] = (uint8_t) offset; out[op + 2] = (uint8_t) (offset >> 8);
+        }
+        op += 3;
+    }
+    return op;
+}
+
+__global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(AccBatch b)
+{
+    extern __shared__ uint16_t sn_tables[];  // kSnWarpsPerCta x kSnTable
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    uint16_t *table = sn_tables + warp * kSnTable;
+
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if ((int64_t) idx >= b.n) break;
+
+        const uint8_t *in = b.src + b.src_off[idx];
+        const int64_t in_len = b.src_len[idx];
+        uint8_t *out = b.dst + b.dst_off[idx];
+        const int64_t out_cap = b.dst_cap[idx];
+        if (in_len > 0x7fffffff || out_cap < 32 + in_len + in_len / 6) {
+            if (lane == 0) { b.out_len[idx] = 0; b.status[idx] = ACC_STATUS(ACC_E_ARGUMENT, ACC_R_MAX_OUTPUT_TOO_SMALL); }
+            continue;
+        }
+        // preamble: varint(uncompressed length) (SnappyRawCompressor.java:383-411)
+        int64_t op = 0;
+        {
+            uint32_t v = (uint32_t) in_len;
+            int nb = v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
+            if (lane < nb) out[lane] = (uint8_t) (((v >> (7 * lane)) & 0x7f) | (lane < nb - 1 ? 0x80 : 0));
+            op = nb;
+        }
+
+        for (int64_t frag = 0; frag < in_len; frag += kSnFragment) {
+            const int64_t frag_limit = (in_len < frag + kSnFragment) ? in_len : frag + kSnFragment;
+            uint32_t *t32 = (uint32_t *) table;
+            for (int i = lane; i < kSnTable / 2; i += 32) t32[i] = 0xffffffffu;  // 0xffff = empty
+            __syncwarp();
+            const uint8_t *base = in + frag;
+            const int64_t flen = frag_limit - frag;
+            // keep the reference's margin: no match starts within the last 15 bytes of a fragment
+            const int64_t fast_limit = flen - 15;
+            int64_t next_emit = 0;
+            int64_t pos = 0;
+            while (pos <= fast_limit) {
+                const int64_t p = pos + lane;
+                bool hit = false;
+                uint32_t cand = 0xffff;
+                uint32_t cur = 0;
+                if (p <= fast_limit) {
+                    cur = ld_u32_unaligned(base + p);
+                    cand = table[snappy_hash(cur)];
+                    if (cand != 0xffff && cand < p && ld_u32_unaligned(base + cand) == cur) hit = true;
+                }
+                __syncwarp();
+                // position 65535 cannot be stored (0xffff = empty); it is never a match start anyway
+                if (p <= fast_limit && p < 0xffff) table[snappy_hash(cur)] = (uint16_t) p;
+                unsigned hits = __ballot_sync(kFull, hit);
+                if (hits == 0) { pos += 32; continue; }
+                const int first = __ffs(hits) - 1;
+                const int64_t mpos = pos + first;
+                const int64_t ref = __shfl_sync(kFull, cand, first);
+                int64_t mlen = 4;
+                for (;;) {
+                    int64_t q = mpos + mlen + lane;
+                    bool same = (q < flen) && (base[q] == base[ref + mlen + lane]);
+                    unsigned eq = __ballot_sync(kFull, same);
+                    if (eq == kFull) { mlen += 32; continue; }
+                    mlen += __ffs(~eq) - 1;
+                    break;
+                }
+                if (mpos > next_emit) op = snappy_emit_literal(out, op, base + next_emit, mpos - next_emit, lane);
+                op = snappy_emit_copy(out, op, (uint32_t) (mpos - ref), mlen, lane);
+                pos = mpos + mlen;
+                next_emit = pos;
+                __syncwarp();
+            }
+            if (next_emit < flen) op = snappy_emit_literal(out, op, base + next_emit, flen - next_emit, lane);
+            __syncwarp();
+        }
+        if (lane == 0) { b.out_len[idx] = op; b.status[idx] = 0; }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    if (ctas_per_sm <= 0) ctas_per_sm = 8;
+    int64_t ctas = (b.n + 7) / 8;
+    int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    snappy_decompress_kernel<<<(unsigned) ctas, 256, 0, st>>>(b);
+}
+
+void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st)
+{
+    const int smem = kSnWarpsPerCta * kSnTable * (int) sizeof(uint16_t);
+    cudaFuncSetAttribute(snappy_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // per device, cheap
+    int64_t ctas = (b.n + kSnWarpsPerCta - 1) / kSnWarpsPerCta;
+    int64_t max_ctas = (int64_t) sm_count * 3;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    snappy_compress_kernel<<<(unsigned) ctas, kSnWarpsPerCta * 32, smem, st>>>(b);
+}
