@@ -255,14 +255,21 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
     int32_t r = enqueue(c, op, b, st, seed);
     if (r != 0) return r;
     CU_TRY(cudaMemcpyAsync(h + 4 * n, c->d_idx + 4 * n, (size_t) (n * 8 + n * 4), cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
-    if (has_dst && dst_bytes > 0) {
-        if (op == ACC_OP_LZ4_DECOMPRESS || op == ACC_OP_SNAPPY_DECOMPRESS || op == ACC_OP_ZSTD_DECOMPRESS || n > 1) {
-            CU_TRY(cudaMemcpyAsync((uint8_t *) dst_base + dst_lo, c->d_dst + dst_pad, (size_t) dst_bytes, cudaMemcpyDeviceToHost, st),
-                   return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+    const bool is_compress = op == ACC_OP_LZ4_COMPRESS || op == ACC_OP_SNAPPY_COMPRESS || op == ACC_OP_ZSTD_COMPRESS;
+    if (has_dst && dst_bytes > 0 && !(is_compress && n == 1)) {
+        // copy back every block's [dst_off, dst_off + dst_cap) window and nothing outside of them: windows that
+        // touch are merged into one transfer (a gap-free batch is a single D2H copy)
+        int64_t run_lo = dst_off[0], run_hi = dst_off[0] + dst_cap[0];
+        for (int64_t i = 1; i <= n; i++) {
+            if (i < n && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
+            if (run_hi > run_lo)
+                CU_TRY(cudaMemcpyAsync((uint8_t *) dst_base + run_lo, c->d_dst + dst_pad + (run_lo - dst_lo), (size_t) (run_hi - run_lo),
+                                       cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+            if (i < n) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
         }
     }
     CU_TRY(cudaStreamSynchronize(st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
-    if (has_dst && dst_bytes > 0 && !(op == ACC_OP_LZ4_DECOMPRESS || op == ACC_OP_SNAPPY_DECOMPRESS || op == ACC_OP_ZSTD_DECOMPRESS || n > 1)) {
+    if (has_dst && dst_bytes > 0 && is_compress && n == 1) {
         // single compress call: copy back only the bytes produced
         int64_t produced = h[4 * n];
         int32_t stt = ((int32_t *) (h + 5 * n))[0];

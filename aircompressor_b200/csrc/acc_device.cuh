@@ -58,7 +58,9 @@ __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p)
 // Warp-cooperative copy of n bytes, src and dst do not overlap (or src is entirely final data).
 // Short runs (the common case on LZ sequences) take one predicated byte move per lane; long runs use
 // 16-byte stores with the source re-aligned through funnel shifts.
-__device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n, int lane)
+// NOTE: no __restrict__ on src -- match copies read bytes this kernel wrote earlier, which must not go
+// through the non-coherent (ld.global.nc) path.
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int64_t n, int lane)
 {
     if (n <= 64) {
         if (lane < n) dst[lane] = src[lane];

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                     uint64_t v = ld_u64_unaligned(in + p);
                     uint32_t h = lz4_hash5(v);
                     cand = table[h];
-                    if (cand >= 0 && p - cand <= 65535 && ld_u32_unaligned(in + cand) == (uint32_t) v) hit = true;
+                    if (cand >= 0 && cand < p && p - cand <= 65535 && ld_u32_unaligned(in + cand) == (uint32_t) v) hit = true;
                 }
                 __syncwarp();
                 // insert after the lookups so that lanes see the table as of the batch start

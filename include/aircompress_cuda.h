@@ -120,7 +120,8 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
 
 /*
  * block i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes at most dst_cap[i] bytes at
- * dst_base + dst_off[i].  `stream` is a CUstream/cudaStream_t handle (0 = the context's own stream);
+ * dst_base + dst_off[i].  `stream` is a CUstream/cudaStream_t handle (0 = the context's own non-blocking
+ * stream; pass 1 (cudaStreamLegacy) or 2 (cudaStreamPerThread) to target CUDA's default streams);
  * with ACC_F_DEVICE_POINTERS the work is only enqueued.  Without it the library copies host->device,
  * runs, copies results back and synchronises before returning.
  */

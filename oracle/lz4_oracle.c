@@ -7,6 +7,16 @@
 #include "oracle.h"
 #include <string.h>
 
+/* forward LZ77 copy with byte-copy semantics; 8 bytes at a time when the distance allows (the Java code
+ * wild-copies longs too), never writing past dst+len */
+static inline void orc_match_copy(uint8_t *dst, const uint8_t *src, int64_t len)
+{
+    int64_t dist = dst - src;
+    if (dist >= 8) {
+        while (len >= 8) { uint64_t v; memcpy(&v, src, 8); memcpy(dst, &v, 8); dst += 8; src += 8; len -= 8; }
+    }
+    while (len-- > 0) *dst++ = *src++;
+}
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
@@ -229,7 +239,7 @@ int64_t orc_lz4_decompress(const uint8_t *in, int64_t in_len, uint8_t *out, int6
             if (match_output_limit > out_cap - LAST_LITERALS) FAIL(input, ORC_R_LAST5_LITERALS);
         }
         /* :146-192 -- overlap-safe copy; the kept bytes equal a forward byte-by-byte copy */
-        for (int64_t i = 0; i < match_length; i++) out[output + i] = out[match + i];
+        orc_match_copy(out + output, out + match, match_length);
         output = match_output_limit;
     }
     return output;

@@ -6,6 +6,16 @@
 #include "oracle.h"
 #include <string.h>
 
+/* forward LZ77 copy with byte-copy semantics; 8 bytes at a time when the distance allows (the Java code
+ * wild-copies longs too), never writing past dst+len */
+static inline void orc_match_copy(uint8_t *dst, const uint8_t *src, int64_t len)
+{
+    int64_t dist = dst - src;
+    if (dist >= 8) {
+        while (len >= 8) { uint64_t v; memcpy(&v, src, 8); memcpy(dst, &v, 8); dst += 8; src += 8; len -= 8; }
+    }
+    while (len-- > 0) *dst++ = *src++;
+}
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint16_t ld16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
@@ -260,7 +270,7 @@ int64_t orc_snappy_decompress(const uint8_t *in0, int64_t in_len0, uint8_t *out,
             if (match_offset <= 0) FAIL(input);                                                     /* :151-153 */
             int64_t match = output - match_offset;
             if (match < 0 || output + length > out_cap) FAIL(input);                                /* :156-158 */
-            for (int32_t i = 0; i < length; i++) out[output + i] = out[match + i];                  /* :164-214 forward-copy semantics */
+            orc_match_copy(out + output, out + match, length);                  /* :164-214 forward-copy semantics */
             output += length;
         }
     }
