@@ -197,6 +197,8 @@ class ZstdCudaDecompressor(Decompressor):
         _verify_range(src, offset, length)
         off = C.c_int64(0)
         r = self._L.acc_zstd_frame_content_size(src.ctypes.data + offset, length, C.byref(off))
+        if r == -1:
+            return -1  # frame does not record its content size (FrameHeader.contentSize == -1 in the Java)
         if r < 0:
             _raise_for(int(-r), off.value)
         return int(r)

@@ -30,7 +30,7 @@ struct acc_ctx {
 
 static thread_local int32_t t_init_error = 0;
 static const char *zstd_reason_text(int32_t reason);   // zstd_host.inc
-static int64_t zstd_scratch_bytes(int32_t op, int64_t n);
+static int64_t zstd_scratch_bytes(int32_t op, int64_t n, int sm_count);
 
 #define CU_TRY(expr, fail_stmt) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail_stmt; } } while (0)
 
@@ -184,7 +184,7 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
         case ACC_OP_ZSTD_COMPRESS:
         case ACC_OP_ZSTD_DECOMPRESS: {
-            int64_t need = zstd_scratch_bytes(op, b.n);
+            int64_t need = zstd_scratch_bytes(op, b.n, c->sm_count);
             if (!grow(&c->d_scratch, &c->d_scratch_cap, need, false)) return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
             if (op == ACC_OP_ZSTD_COMPRESS) acc_launch_zstd_compress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);
             else acc_launch_zstd_decompress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);

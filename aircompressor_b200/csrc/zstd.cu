@@ -1,4 +1,4 @@
-// zstd.cu -- Zstandard kernels (placeholder: reports ACC_E_UNSUPPORTED per block until the real kernels land).
+// zstd.cu -- placeholder for the Zstandard encode kernel (reports ACC_E_UNSUPPORTED per block until it lands).
 #include "acc_device.cuh"
 
 namespace {
@@ -9,11 +9,8 @@ __global__ void zstd_unsupported_kernel(AccBatch b)
 }
 }  // namespace
 
-void acc_launch_zstd_decompress(const AccBatch &b, int, cudaStream_t st, void *, int64_t)
-{
-    zstd_unsupported_kernel<<<(unsigned) ((b.n + 255) / 256), 256, 0, st>>>(b);
-}
 void acc_launch_zstd_compress(const AccBatch &b, int, cudaStream_t st, void *, int64_t)
 {
     zstd_unsupported_kernel<<<(unsigned) ((b.n + 255) / 256), 256, 0, st>>>(b);
 }
+int64_t acc_zstd_enc_scratch_bytes(int) { return 0; }

@@ -1,0 +1,688 @@
+// zstd_dec.cu -- Zstandard frame decode kernel for sm_100a.
+//
+// Replaces ZstdFrameDecompressor.decompress (zstd/ZstdFrameDecompressor.java:135-210) and everything it
+// calls: frame/block headers (:860-940, :163-190), literals (:708-858 + zstd/Huffman.java:52-324),
+// sequence tables (:609-676 + zstd/FseTableReader.java:27-168), sequence decode + execution (:312-516),
+// XXH64 frame checksum (:194-206).  Output and accept/reject decisions are bit-exact with the Java
+// decoder (offsets in error reports are relative to the input start).
+//
+// Mapping: one warp per input (all frames of the input, all blocks of a frame, in order).  Per warp in
+// shared memory: the Huffman decode table (4096 x u16), three FSE decode tables (512/512/256 x u32) and
+// a 32-entry sequence batch.  Lane 0 parses headers and walks the FSE state chain, lanes 0-3 decode the
+// four Huffman streams, all 32 lanes build tables and execute literal / match copies.
+#include "zstd_common.cuh"
+#include "xxh64_device.cuh"
+
+namespace {
+using namespace zs;
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kSeqBatch = 32;
+
+struct WarpSmem {
+    uint16_t huf[4096];       // symbol | nbits << 8
+    uint32_t ll[512], ml[512], of[256];
+    uint32_t wt[64];          // FSE table of the Huffman weights (must not clobber ll/ml/of: repeat mode reuses them)
+    int16_t norm[256];
+    int16_t next[256];
+    uint8_t scratch[512];     // symbol spread buffer / Huffman weights
+    int32_t seq_ll[kSeqBatch], seq_ml[kSeqBatch], seq_of[kSeqBatch];
+    int32_t ranks[16];
+};
+
+struct Ctl {   // lane-0 results broadcast through registers
+    int32_t reason;
+    int64_t err_off;
+};
+
+#define ZFAIL(reason_, off_) do { ctl.reason = (reason_); ctl.err_off = (off_); return -1; } while (0)
+#define ZCHECK(cond, off_, reason_) do { if (!(cond)) ZFAIL(reason_, off_); } while (0)
+
+// FseTableReader.readFseTable :27-160 (single thread).  Returns bytes consumed or -1.
+__device__ int64_t fse_read_table(uint32_t *table, int *table_log_out, const uint8_t *in, int64_t in_addr, int64_t in_limit, int max_symbol,
+                                  int max_table_log, WarpSmem &sm, Ctl &ctl)
+{
+    int16_t *norm = sm.norm;
+    int64_t input = in_addr;
+    ZCHECK(in_limit - in_addr >= 4, input, R_NOT_ENOUGH_INPUT);
+    int symbol_number = 0;
+    bool previous_is_zero = false;
+    uint32_t bit_stream = ld32u(in + input);
+    int table_log = (int) (bit_stream & 0xF) + 5;
+    int nbits = table_log + 1;
+    bit_stream >>= 4;
+    int bit_count = 4;
+    ZCHECK(table_log <= max_table_log, input, R_FSE_TABLE_TOO_LARGE);
+    int remaining = (1 << table_log) + 1;
+    int threshold = 1 << table_log;
+    while (remaining > 1 && symbol_number <= max_symbol) {
+        if (previous_is_zero) {
+            int n0 = symbol_number;
+            while ((bit_stream & 0xFFFF) == 0xFFFF) {
+                n0 += 24;
+                if (input < in_limit - 5) { input += 2; bit_stream = ld32u(in + input) >> (bit_count & 31); }
+                else { bit_stream >>= 16; bit_count += 16; }
+            }
+            while ((bit_stream & 3) == 3) { n0 += 3; bit_stream >>= 2; bit_count += 2; }
+            n0 += (int) (bit_stream & 3);
+            bit_count += 2;
+            ZCHECK(n0 <= max_symbol, input, R_SYMBOL_TOO_LARGE);
+            while (symbol_number < n0) norm[symbol_number++] = 0;
+            if (input <= in_limit - 7 || input + (bit_count >> 3) <= in_limit - 4) {
+                input += bit_count >> 3;
+                bit_count &= 7;
+                bit_stream = ld32u(in + input) >> bit_count;
+            }
+            else {
+                bit_stream >>= 2;
+            }
+        }
+        int16_t max = (int16_t) ((2 * threshold - 1) - remaining);
+        int16_t count;
+        if ((int32_t) (bit_stream & (uint32_t) (threshold - 1)) < max) {
+            count = (int16_t) (bit_stream & (uint32_t) (threshold - 1));
+            bit_count += nbits - 1;
+        }
+        else {
+            count = (int16_t) (bit_stream & (uint32_t) (2 * threshold - 1));
+            if (count >= threshold) count = (int16_t) (count - max);
+            bit_count += nbits;
+        }
+        count--;
+        remaining -= count < 0 ? -count : count;
+        norm[symbol_number++] = count;
+        previous_is_zero = count == 0;
+        while (remaining < threshold) { nbits--; threshold >>= 1; }
+        if (input <= in_limit - 7 || input + (bit_count >> 3) <= in_limit - 4) {
+            input += bit_count >> 3;
+            bit_count &= 7;
+        }
+        else {
+            bit_count -= (int) (8 * (in_limit - 4 - input));
+            input = in_limit - 4;
+        }
+        bit_stream = ld32u(in + input) >> (bit_count & 31);
+    }
+    ZCHECK(remaining == 1 && bit_count <= 32, input, R_CORRUPTED);
+    int max_sym = symbol_number - 1;
+    ZCHECK(max_sym <= 255, input, R_TOO_MANY_SYMBOLS);
+    input += (bit_count + 7) >> 3;
+    if (!fse_build_dtable(table, norm, max_sym, table_log, sm.scratch, sm.next)) ZFAIL(R_CORRUPTED, input);
+    *table_log_out = table_log;
+    return input - in_addr;
+}
+
+// FiniteStateEntropy.decompress :38-151 (Huffman weights, single thread).  Returns symbol count or -1.
+__device__ int fse_decompress_weights(const uint32_t *table, int log2, const uint8_t *in, int64_t in_addr, int64_t in_limit, uint8_t *out, int out_cap,
+                                      Ctl &ctl)
+{
+    BitReader b;
+    int64_t eo = 0;
+    int r = br_init(b, in, in_addr, in_limit, &eo);
+    if (r) ZFAIL(r, eo);
+    int output = 0;
+    int state1 = (int) peek_bits(b.consumed, b.bits, log2); b.consumed += log2;
+    br_load(b);
+    int state2 = (int) peek_bits(b.consumed, b.bits, log2); b.consumed += log2;
+    br_load(b);
+#define FSE_SYM(st) (uint8_t) (table[st] >> 24)
+#define FSE_STEP(st) do { uint32_t e_ = table[st]; int nb_ = (e_ >> 16) & 0xFF; st = (int) ((e_ & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb_)); b.consumed += nb_; } while (0)
+    while (output <= out_cap - 4) {
+        out[output] = FSE_SYM(state1); FSE_STEP(state1);
+        out[output + 1] = FSE_SYM(state2); FSE_STEP(state2);
+        out[output + 2] = FSE_SYM(state1); FSE_STEP(state1);
+        out[output + 3] = FSE_SYM(state2); FSE_STEP(state2);
+        output += 4;
+        if (br_load(b)) break;
+    }
+    for (;;) {
+        ZCHECK(output <= out_cap - 2, in_addr, R_FSE_OUTPUT_TOO_SMALL);
+        out[output++] = FSE_SYM(state1); FSE_STEP(state1);
+        br_load(b);
+        if (b.overflow) { out[output++] = FSE_SYM(state2); break; }
+        ZCHECK(output <= out_cap - 2, in_addr, R_FSE_OUTPUT_TOO_SMALL);
+        out[output++] = FSE_SYM(state2); FSE_STEP(state2);
+        br_load(b);
+        if (b.overflow) { out[output++] = FSE_SYM(state1); break; }
+    }
+#undef FSE_STEP
+#undef FSE_SYM
+    return output;
+}
+
+struct FrameState {
+    int huf_log;              // -1 = no Huffman table loaded
+    int ll_log, of_log, ml_log;   // -1 = no table yet in this frame
+    int32_t prev[3];
+};
+
+// Huffman.readTable :52-128.  Lane 0 reads the weights, all lanes fill the table.  Returns bytes consumed or -1 (uniform).
+__device__ int64_t huf_read_table(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int size, Ctl &ctl, int lane)
+{
+    uint8_t *weights = sm.scratch;   // 257 needed; scratch has 512
+    int32_t *ranks = sm.ranks;
+    int64_t ret = 0;
+    int number_of_symbols = 0, table_log = 0;
+    if (lane == 0) {
+        ret = [&]() -> int64_t {
+            for (int i = 0; i < 16; i++) ranks[i] = 0;
+            int64_t input = in_addr;
+            ZCHECK(size > 0, input, R_NOT_ENOUGH_INPUT);
+            int input_size = in[input++];
+            int output_size;
+            if (input_size >= 128) {
+                output_size = input_size - 127;
+                input_size = (output_size + 1) / 2;
+                ZCHECK(input_size + 1 <= size, input, R_NOT_ENOUGH_INPUT);
+                ZCHECK(output_size <= 256, input, R_CORRUPTED);
+                for (int i = 0; i < output_size; i += 2) {
+                    int v = in[input + i / 2];
+                    weights[i] = (uint8_t) (v >> 4);
+                    weights[i + 1] = (uint8_t) (v & 15);
+                }
+            }
+            else {
+                ZCHECK(input_size + 1 <= size, input, R_NOT_ENOUGH_INPUT);
+                int64_t limit = input + input_size;
+                int wlog = 0;
+                int64_t used = fse_read_table(sm.wt, &wlog, in, input, limit, 255, 6, sm, ctl);
+                if (used < 0) return -1;
+                input += used;
+                int n = fse_decompress_weights(sm.wt, wlog, in, input, limit, weights, 256, ctl);
+                if (n < 0) return -1;
+                output_size = n;
+                ZCHECK(output_size <= 255, input, R_CORRUPTED);   // the Java indexes weights[outputSize] in a byte[256]
+            }
+            int total_weight = 0;
+            for (int i = 0; i < output_size; i++) {
+                ZCHECK(weights[i] <= 12, input, R_CORRUPTED);
+                ranks[weights[i]]++;
+                total_weight += (1 << weights[i]) >> 1;
+            }
+            ZCHECK(total_weight != 0, input, R_CORRUPTED);
+            int tl = highbit((uint32_t) total_weight) + 1;
+            ZCHECK(tl <= 12, input, R_CORRUPTED);
+            int rest = (1 << tl) - total_weight;
+            ZCHECK((rest & (rest - 1)) == 0, input, R_CORRUPTED);
+            int last_weight = highbit((uint32_t) rest) + 1;
+            weights[output_size] = (uint8_t) last_weight;
+            ranks[last_weight]++;
+            int next_rank_start = 0;
+            for (int i = 1; i < tl + 1; ++i) {
+                int current = next_rank_start;
+                next_rank_start += ranks[i] << (i - 1);
+                ranks[i] = current;
+            }
+            // per-symbol start positions (serial prefix in symbol order, like the Java loop); stored in norm[]
+            int r1_end = 0;
+            for (int n = 0; n < output_size + 1; n++) {
+                int w = weights[n];
+                sm.norm[n] = (int16_t) ranks[w];
+                ranks[w] += (1 << w) >> 1;
+            }
+            r1_end = ranks[1];
+            ZCHECK(r1_end >= 2 && (r1_end & 1) == 0, input, R_CORRUPTED);
+            number_of_symbols = output_size + 1;
+            table_log = tl;
+            return input_size + 1;
+        }();
+    }
+    ret = __shfl_sync(kFull, ret, 0);
+    if (ret < 0) { ctl.reason = __shfl_sync(kFull, ctl.reason, 0); ctl.err_off = __shfl_sync(kFull, ctl.err_off, 0); return -1; }
+    number_of_symbols = __shfl_sync(kFull, number_of_symbols, 0);
+    table_log = __shfl_sync(kFull, table_log, 0);
+    __syncwarp();
+    // fill: symbol n covers [start, start + (1 << w) >> 1)
+    for (int n = 0; n < number_of_symbols; n++) {
+        int w = weights[n];
+        int length = (1 << w) >> 1;
+        int start = (uint16_t) sm.norm[n];
+        uint16_t e = (uint16_t) (n | ((table_log + 1 - w) << 8));
+        for (int i = lane; i < length; i += 32) sm.huf[start + i] = e;
+    }
+    __syncwarp();
+    fs.huf_log = table_log;
+    return ret;
+}
+
+// One Huffman stream decoded by one thread (Huffman.decodeTail semantics, zstd/Huffman.java:291-317).
+__device__ int huf_decode_stream(const uint16_t *huf, int tl, const uint8_t *in, int64_t start, int64_t end, uint8_t *out, int64_t n, int64_t *err_off)
+{
+    BitReader b;
+    int r = br_init(b, in, start, end, err_off);
+    if (r) return r;
+    int64_t o = 0;
+    while (o < n) {
+        if (br_load(b)) break;
+        uint32_t e = huf[(int) peek_bits_fast(b.consumed, b.bits, tl)];
+        out[o++] = (uint8_t) e;
+        b.consumed += e >> 8;
+    }
+    while (o < n) {
+        uint32_t e = huf[(int) peek_bits_fast(b.consumed, b.bits, tl)];
+        out[o++] = (uint8_t) e;
+        b.consumed += e >> 8;
+    }
+    if (!(b.start == b.cur && b.consumed == 64)) { *err_off = start; return R_BITSTREAM_NOT_CONSUMED; }
+    return 0;
+}
+
+struct Literals {
+    const uint8_t *ptr;   // raw / decoded literals; unused for RLE
+    int64_t size;
+    int rle;              // -1 = not RLE, else the byte
+};
+
+// copy `n` literal bytes starting at literal position `pos` to dst (warp-cooperative)
+__device__ __forceinline__ void copy_literals(uint8_t *dst, const Literals &lit, int64_t pos, int64_t n, int lane)
+{
+    if (lit.rle >= 0) {
+        for (int64_t i = lane; i < n; i += 32) dst[i] = (uint8_t) lit.rle;
+    }
+    else {
+        warp_copy(dst, lit.ptr + pos, n, lane);
+    }
+}
+
+// decodes one compressed block (ZstdFrameDecompressor.decodeCompressedBlock :265-310 + decompressSequences :312-516).
+// Returns bytes produced or -1.  `out`/`out_pos` are relative to the start of the caller's output buffer.
+__device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int block_size, uint8_t *out,
+                                           int64_t out_pos, int64_t out_cap, int32_t window_size, uint8_t *lit_scratch, Ctl &ctl, int lane)
+{
+    int64_t input = in_addr;
+    const int64_t block_end = in_addr + block_size;
+    ZCHECK(block_size <= kMaxBlock, input, R_EXPECTED_TABLE);
+    ZCHECK(block_size >= 3, input, R_BLOCK_TOO_SMALL);
+    Literals lit;
+    lit.rle = -1; lit.ptr = nullptr; lit.size = 0;
+    const int b0 = in[input];
+    const int lit_type = b0 & 3;
+    const int size_format = (b0 >> 2) & 3;
+    if (lit_type == 0 || lit_type == 1) {
+        // decodeRawLiterals :812-858 / decodeRleLiterals :776-810
+        int32_t lsize;
+        if (size_format == 0 || size_format == 2) { lsize = b0 >> 3; input += 1; }
+        else if (size_format == 1) { lsize = (int32_t) (ld16u(in + input) >> 4); input += 2; }
+        else {
+            if (lit_type == 1) ZCHECK(block_size >= 4, input, R_NOT_ENOUGH_INPUT);
+            lsize = (int32_t) (((uint32_t) in[input] | (ld16u(in + input + 1) << 8)) >> 4);
+            input += 3;
+        }
+        if (lit_type == 0) {
+            ZCHECK(input + lsize <= block_end, input, R_NOT_ENOUGH_INPUT);
+            lit.ptr = in + input;
+            lit.size = lsize;
+            input += lsize;
+        }
+        else {
+            ZCHECK(lsize <= kMaxBlock, input, R_OUTPUT_EXCEEDS_BLOCK);
+            lit.rle = in[input++];
+            lit.size = lsize;
+        }
+    }
+    else {
+        if (lit_type == 3) ZCHECK(fs.huf_log != -1, input, R_DICTIONARY_CORRUPTED);
+        // decodeCompressedLiterals :708-774
+        ZCHECK(block_size >= 5, input, R_NOT_ENOUGH_INPUT);
+        int32_t comp_size, unc_size, header_size;
+        bool single = false;
+        if (size_format == 0 || size_format == 1) {
+            single = size_format == 0;
+            uint32_t hd = ld32u(in + input);
+            header_size = 3; unc_size = (int32_t) ((hd >> 4) & 0x3FF); comp_size = (int32_t) ((hd >> 14) & 0x3FF);
+        }
+        else if (size_format == 2) {
+            uint32_t hd = ld32u(in + input);
+            header_size = 4; unc_size = (int32_t) ((hd >> 4) & 0x3FFF); comp_size = (int32_t) ((hd >> 18) & 0x3FFF);
+        }
+        else {
+            uint64_t hd = (uint64_t) in[input] | ((uint64_t) ld32u(in + input + 1) << 8);
+            header_size = 5; unc_size = (int32_t) ((hd >> 4) & 0x3FFFF); comp_size = (int32_t) ((hd >> 22) & 0x3FFFF);
+        }
+        ZCHECK(unc_size <= kMaxBlock, input, R_BLOCK_EXCEEDS_MAX);
+        ZCHECK(header_size + comp_size <= block_size, input, R_CORRUPTED);
+        input += header_size;
+        const int64_t lit_limit = input + comp_size;
+        if (lit_type != 3) {
+            int64_t used = huf_read_table(sm, fs, in, input, comp_size, ctl, lane);
+            if (used < 0) return -1;
+            input += used;
+        }
+        // streams
+        int reason = 0;
+        int64_t eo = 0;
+        const int tl = fs.huf_log;
+        if (single) {
+            if (lane == 0) reason = huf_decode_stream(sm.huf, tl, in, input, lit_limit, lit_scratch, unc_size, &eo);
+        }
+        else {
+            // decode4Streams :166-289
+            if (lit_limit - input < 10) { reason = R_CORRUPTED; eo = input; }
+            else {
+                int64_t s1 = input + 6;
+                int64_t s2 = s1 + ld16u(in + input), s3 = s2 + ld16u(in + input + 2), s4 = s3 + ld16u(in + input + 4);
+                if (!(s2 < s3 && s3 < s4 && s4 < lit_limit)) { reason = R_CORRUPTED; eo = input; }
+                else if (lane < 4) {
+                    int64_t seg = ((int64_t) unc_size + 3) / 4;
+                    int64_t st = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
+                    int64_t en = lane == 0 ? s2 : lane == 1 ? s3 : lane == 2 ? s4 : lit_limit;
+                    int64_t o0 = seg * lane;
+                    int64_t n = lane < 3 ? seg : (int64_t) unc_size - 3 * seg;
+                    if (n < 0) n = 0;   // tiny 4-stream sections: the Java decodes nothing from stream 4 but still wants it fully consumed
+                    reason = huf_decode_stream(sm.huf, tl, in, st, en, lit_scratch + o0, n, &eo);
+                }
+            }
+        }
+        // first failing lane (lowest stream index) wins, like the Java's stream-by-stream tail checks
+        unsigned bad = __ballot_sync(kFull, reason != 0);
+        if (bad) {
+            int src = __ffs(bad) - 1;
+            ctl.reason = __shfl_sync(kFull, reason, src);
+            ctl.err_off = __shfl_sync(kFull, eo, src);
+            return -1;
+        }
+        __syncwarp();
+        lit.ptr = lit_scratch;
+        lit.size = unc_size;
+        input = lit_limit;
+    }
+    ZCHECK(window_size <= (1 << 23), input, R_WINDOW_TOO_LARGE);
+
+    // ---- sequences section ----
+    int64_t output = out_pos;
+    int64_t lit_pos = 0;
+    ZCHECK(block_end - input >= 1, input, R_NOT_ENOUGH_INPUT);
+    int32_t seq_count = in[input++];
+    if (seq_count != 0) {
+        if (seq_count == 255) {
+            ZCHECK(input + 2 <= block_end, input, R_NOT_ENOUGH_INPUT);
+            seq_count = (int32_t) ld16u(in + input) + 0x7F00;
+            input += 2;
+        }
+        else if (seq_count > 127) {
+            ZCHECK(input < block_end, input, R_NOT_ENOUGH_INPUT);
+            seq_count = ((seq_count - 128) << 8) + in[input++];
+        }
+        ZCHECK(input + 4 <= block_end, input, R_NOT_ENOUGH_INPUT);
+        const uint32_t type = in[input++];
+        // computeLiteralsTable / computeOffsetsTable / computeMatchLengthTable :609-676 (lane 0 builds, result broadcast)
+        int64_t tb_ret = 0;
+        int lg[3] = {fs.ll_log, fs.of_log, fs.ml_log};
+        if (lane == 0) {
+            tb_ret = [&]() -> int64_t {
+                const int types[3] = {(int) (type >> 6), (int) ((type >> 4) & 3), (int) ((type >> 2) & 3)};
+                uint32_t *tables[3] = {sm.ll, sm.of, sm.ml};
+                const int max_sym[3] = {35, 28, 52};
+                const int max_log[3] = {9, 8, 9};
+                const int def_log[3] = {6, 5, 6};
+                for (int k = 0; k < 3; k++) {
+                    if (types[k] == 1) {
+                        ZCHECK(input < block_end, input, R_NOT_ENOUGH_INPUT);
+                        int8_t value = (int8_t) in[input++];
+                        ZCHECK(value <= max_sym[k] && value >= 0, input, R_VALUE_EXCEEDS_MAX);
+                        tables[k][0] = fse_entry(0, 0, value);
+                        lg[k] = 0;
+                    }
+                    else if (types[k] == 0) {
+                        const int16_t *def = k == 0 ? kDefLL : k == 1 ? kDefOF : kDefML;
+                        for (int s = 0; s <= max_sym[k]; s++) sm.norm[s] = def[s];
+                        fse_build_dtable(tables[k], sm.norm, max_sym[k], def_log[k], sm.scratch, sm.next);
+                        lg[k] = def_log[k];
+                    }
+                    else if (types[k] == 3) {
+                        ZCHECK(lg[k] >= 0, input, R_EXPECTED_TABLE);
+                    }
+                    else {
+                        int tlog = 0;
+                        int64_t used = fse_read_table(tables[k], &tlog, in, input, block_end, max_sym[k], max_log[k], sm, ctl);
+                        if (used < 0) return -1;
+                        input += used;
+                        lg[k] = tlog;
+                    }
+                }
+                return input;
+            }();
+        }
+        tb_ret = __shfl_sync(kFull, tb_ret, 0);
+        if (tb_ret < 0) { ctl.reason = __shfl_sync(kFull, ctl.reason, 0); ctl.err_off = __shfl_sync(kFull, ctl.err_off, 0); return -1; }
+        input = tb_ret;
+        fs.ll_log = __shfl_sync(kFull, lg[0], 0);
+        fs.of_log = __shfl_sync(kFull, lg[1], 0);
+        fs.ml_log = __shfl_sync(kFull, lg[2], 0);
+        __syncwarp();
+
+        // lane 0 owns the bit reader and the three FSE states; sequences are produced in batches of 32 and
+        // executed by the whole warp.
+        BitReader b;
+        int ll_state = 0, of_state = 0, ml_state = 0;
+        int32_t p0 = fs.prev[0], p1 = fs.prev[1], p2 = fs.prev[2];
+        int init_reason = 0;
+        int64_t init_eo = 0;
+        if (lane == 0) {
+            init_reason = br_init(b, in, input, block_end, &init_eo);
+            if (!init_reason) {
+                ll_state = (int) peek_bits(b.consumed, b.bits, fs.ll_log); b.consumed += fs.ll_log;
+                of_state = (int) peek_bits(b.consumed, b.bits, fs.of_log); b.consumed += fs.of_log;
+                ml_state = (int) peek_bits(b.consumed, b.bits, fs.ml_log); b.consumed += fs.ml_log;
+            }
+        }
+        init_reason = __shfl_sync(kFull, init_reason, 0);
+        if (init_reason) { ctl.reason = init_reason; ctl.err_off = __shfl_sync(kFull, init_eo, 0); return -1; }
+
+        int32_t remaining = seq_count;
+        bool stop = false;   // overflow with sequenceCount == 0 -> leave the loop (Java `break`)
+        while (remaining > 0 && !stop) {
+            int produced = 0;
+            int fail = 0;
+            if (lane == 0) {
+                while (produced < kSeqBatch && remaining > 0) {
+                    remaining--;
+                    br_load(b);
+                    if (b.overflow) {
+                        if (remaining != 0) fail = R_NOT_ALL_SEQUENCES;
+                        stop = true;
+                        break;
+                    }
+                    const uint32_t el = sm.ll[ll_state], em = sm.ml[ml_state], eof = sm.of[of_state];
+                    const int ll_code = el >> 24, ml_code = em >> 24, of_code = eof >> 24;
+                    const int ll_bits = kLLBits[ll_code], ml_bits = kMLBits[ml_code], of_bits = of_code;
+                    int32_t offset = of_base(of_code);
+                    if (of_code > 0) { offset += (int32_t) peek_bits(b.consumed, b.bits, of_bits); b.consumed += of_bits; }
+                    if (of_code <= 1) {
+                        if (ll_code == 0) offset++;
+                        if (offset != 0) {
+                            int32_t temp = (offset == 3) ? p0 - 1 : (offset == 1 ? p1 : p2);
+                            if (temp == 0) temp = 1;
+                            if (offset != 1) p2 = p1;
+                            p1 = p0;
+                            p0 = temp;
+                            offset = temp;
+                        }
+                        else {
+                            offset = p0;
+                        }
+                    }
+                    else {
+                        p2 = p1; p1 = p0; p0 = offset;
+                    }
+                    int32_t match_length = kMLBase[ml_code];
+                    if (ml_code > 31) { match_length += (int32_t) peek_bits(b.consumed, b.bits, ml_bits); b.consumed += ml_bits; }
+                    int32_t lit_length = kLLBase[ll_code];
+                    if (ll_code > 15) { lit_length += (int32_t) peek_bits(b.consumed, b.bits, ll_bits); b.consumed += ll_bits; }
+                    if (ll_bits + ml_bits + of_bits > 64 - 7 - (9 + 9 + 8)) br_load(b);
+                    int nb;
+                    nb = (el >> 16) & 0xFF; ll_state = (int) ((el & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (em >> 16) & 0xFF; ml_state = (int) ((em & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (eof >> 16) & 0xFF; of_state = (int) ((eof & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    sm.seq_ll[produced] = lit_length;
+                    sm.seq_ml[produced] = match_length;
+                    sm.seq_of[produced] = offset;
+                    produced++;
+                }
+            }
+            produced = __shfl_sync(kFull, produced, 0);
+            fail = __shfl_sync(kFull, fail, 0);
+            remaining = __shfl_sync(kFull, remaining, 0);
+            stop = __shfl_sync(kFull, (int) stop, 0) != 0;
+            __syncwarp();
+            // execute (all lanes, in order)
+            for (int s = 0; s < produced; s++) {
+                const int64_t lit_length = sm.seq_ll[s], match_length = sm.seq_ml[s];
+                const int64_t offset = sm.seq_of[s];
+                const int64_t lit_out_limit = output + lit_length;
+                const int64_t match_out_limit = lit_out_limit + match_length;
+                ZCHECK(match_out_limit <= out_cap, input, R_OUTPUT_TOO_SMALL);
+                const int64_t lit_end = lit_pos + lit_length;
+                ZCHECK(lit_end <= lit.size, input, R_CORRUPTED);
+                ZCHECK(lit_out_limit - offset >= 0, input, R_CORRUPTED);
+                copy_literals(out + output, lit, lit_pos, lit_length, lane);
+                __syncwarp();
+                warp_match_copy(out + lit_out_limit, offset, match_length, lane);
+                __syncwarp();
+                output = match_out_limit;
+                lit_pos = lit_end;
+            }
+            if (fail) ZFAIL(fail, input);
+            __syncwarp();
+        }
+        fs.prev[0] = __shfl_sync(kFull, p0, 0);
+        fs.prev[1] = __shfl_sync(kFull, p1, 0);
+        fs.prev[2] = __shfl_sync(kFull, p2, 0);
+    }
+    // copyLastLiteral :518-525
+    const int64_t last = lit.size - lit_pos;
+    ZCHECK(output + last <= out_cap, input, R_OUTPUT_TOO_SMALL);
+    copy_literals(out + output, lit, lit_pos, last, lane);
+    output += last;
+    __syncwarp();
+    return output - out_pos;
+}
+
+// ZstdFrameDecompressor.decompress :135-210 for one input.  Returns output size or -1.
+__device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_cap, uint8_t *lit_scratch, Ctl &ctl, int lane)
+{
+    if (out_cap == 0) return 0;
+    int64_t input = 0, output = 0;
+    FrameState fs;
+    fs.huf_log = -1;   // a fresh decompressor per call (the Java object would keep its table across calls)
+    while (input < in_len) {
+        fs.prev[0] = 1; fs.prev[1] = 4; fs.prev[2] = 8;
+        fs.ll_log = fs.of_log = fs.ml_log = -1;
+        const int64_t output_start = output;
+        // verifyMagic :949-962
+        ZCHECK(in_len - input >= 4, input, R_NOT_ENOUGH_INPUT);
+        const uint32_t magic = ld32u(in + input);
+        if (magic != 0xFD2FB528u) ZFAIL(magic == 0xFD2FB527u ? R_V07_FORMAT : R_BAD_MAGIC, input);
+        input += 4;
+        // readFrameHeader :860-940
+        const int64_t fh_start = input;
+        ZCHECK(input < in_len, input, R_NOT_ENOUGH_INPUT);
+        const int fhd = in[input++];
+        const bool single_segment = (fhd & 0x20) != 0;
+        const int dict_desc = fhd & 3, cs_desc = fhd >> 6;
+        const int header_size = 1 + (single_segment ? 0 : 1) + (dict_desc == 0 ? 0 : (1 << (dict_desc - 1))) +
+                                (cs_desc == 0 ? (single_segment ? 1 : 0) : (1 << cs_desc));
+        ZCHECK(header_size <= in_len - fh_start, input, R_NOT_ENOUGH_INPUT);
+        int32_t window_size = -1;
+        if (!single_segment) {
+            const int wd = in[input++];
+            const int exponent = wd >> 3, mantissa = wd & 7;
+            const int32_t base = (int32_t) (1u << ((10 + exponent) & 31));
+            window_size = (int32_t) ((uint32_t) base + (uint32_t) (base / 8) * (uint32_t) mantissa);
+        }
+        if (dict_desc != 0) { input += (1 << (dict_desc - 1)); ZFAIL(R_DICTIONARY, input); }
+        input = fh_start + header_size;   // content size field is not needed for decoding
+        const bool has_checksum = (fhd & 4) != 0;
+
+        bool last_block;
+        do {
+            ZCHECK(input + 3 <= in_len, input, R_NOT_ENOUGH_INPUT);
+            const uint32_t header = ld16u(in + input) | ((uint32_t) in[input + 2] << 16);
+            input += 3;
+            last_block = (header & 1) != 0;
+            const int block_type = (header >> 1) & 3;
+            const int32_t block_size = (int32_t) ((header >> 3) & 0x1FFFFF);
+            int64_t decoded;
+            if (block_type == 0) {
+                ZCHECK(input + block_size <= in_len, input, R_NOT_ENOUGH_INPUT);
+                ZCHECK(output + block_size <= out_cap, input, R_OUTPUT_TOO_SMALL);
+                warp_copy(out + output, in + input, block_size, lane);
+                decoded = block_size;
+                input += block_size;
+            }
+            else if (block_type == 1) {
+                ZCHECK(input + 1 <= in_len, input, R_NOT_ENOUGH_INPUT);
+                ZCHECK(output + block_size <= out_cap, input, R_OUTPUT_TOO_SMALL);
+                const uint8_t v = in[input];
+                for (int64_t i = lane; i < block_size; i += 32) out[output + i] = v;
+                decoded = block_size;
+                input += 1;
+            }
+            else if (block_type == 2) {
+                ZCHECK(input + block_size <= in_len, input, R_NOT_ENOUGH_INPUT);
+                decoded = decode_compressed_block(sm, fs, in, input, block_size, out, output, out_cap, window_size, lit_scratch, ctl, lane);
+                if (decoded < 0) return -1;
+                input += block_size;
+            }
+            else {
+                ZFAIL(R_INVALID_BLOCK_TYPE, input);
+            }
+            output += decoded;
+            __syncwarp();
+        }
+        while (!last_block);
+
+        if (has_checksum) {
+            __syncwarp();
+            const uint64_t hash = xxh64_group4(out + output_start, lane < 4 ? output - output_start : 0, 0, lane & 3, 0xFu << (lane & ~3));
+            const uint32_t h32 = (uint32_t) __shfl_sync(kFull, hash, 0);
+            ZCHECK(input + 4 <= in_len, input, R_NOT_ENOUGH_INPUT);
+            if (ld32u(in + input) != h32) ZFAIL(R_BAD_CHECKSUM, input);
+            input += 4;
+        }
+    }
+    return output;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t zsmem[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    WarpSmem &sm = *reinterpret_cast<WarpSmem *>(zsmem + (size_t) warp * sizeof(WarpSmem));
+    uint8_t *lit_scratch = scratch + ((int64_t) blockIdx.x * kWarpsPerCta + warp) * scratch_per_warp;
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if ((int64_t) idx >= b.n) break;
+        Ctl ctl;
+        ctl.reason = 0; ctl.err_off = 0;
+        int64_t r = decode_input(sm, b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx], lit_scratch, ctl, lane);
+        if (lane == 0) {
+            if (r >= 0) { b.out_len[idx] = r; b.status[idx] = 0; }
+            else { b.out_len[idx] = ctl.err_off; b.status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256;
+
+int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * 3; }   // 3 CTAs x 4 warps per SM (shared memory bound)
+
+int64_t acc_zstd_dec_scratch_bytes(int sm_count) { return acc_zstd_dec_grid(sm_count) * kWarpsPerCta * kZstdDecScratchPerWarp; }
+
+void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes)
+{
+    const int smem = kWarpsPerCta * (int) sizeof(WarpSmem);
+    cudaFuncSetAttribute(zstd_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int64_t ctas = (b.n + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t max_ctas = acc_zstd_dec_grid(sm_count);
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    (void) scratch_bytes;
+    zstd_decompress_kernel<<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
+}

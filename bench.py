@@ -173,8 +173,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd"])
     ap.add_argument("--op", default="decompress", choices=["compress", "decompress"])
-    ap.add_argument("--block-kib", type=int, default=64)
-    ap.add_argument("--blocks", type=int, default=65536)
+    ap.add_argument("--block-kib", type=int, default=0, help="default 64 (lz4/snappy) or 128 (zstd)")
+    ap.add_argument("--blocks", type=int, default=0, help="default: 4 GiB of uncompressed data per GPU")
     ap.add_argument("--ref-blocks", type=int, default=8192, help="bounded sample for the CPU arms")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-extra", action="store_true", help="skip the short per-codec side measurements")
@@ -182,6 +182,10 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): no e2e, no cpu baseline, warm-up as given")
     args = ap.parse_args()
+    if args.block_kib == 0:
+        args.block_kib = 128 if args.codec == "zstd" else 64
+    if args.blocks == 0:
+        args.blocks = (4 << 20) // args.block_kib
     if args.impl == "cuda" and not args.profile:
         args.warmup = max(args.warmup, 3)
     if args.profile:

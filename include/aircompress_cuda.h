@@ -101,7 +101,8 @@ int64_t acc_zstd_decompress(acc_ctx *ctx, const void *src, int64_t src_len, void
 /* header-only host helpers: snappy_uncompressed_length (snappy/SnappyNative.java:72-75; Java
  * SnappyRawDecompressor.getUncompressedLength :30-33) and ZSTD_getFrameContentSize
  * (zstd/ZstdNative.java:34; Java ZstdFrameDecompressor.getDecompressedSize :942-947).
- * Return >= 0 or -(status); *err_offset optional. */
+ * Return >= 0 or -(status); *err_offset optional.  acc_zstd_frame_content_size returns -1 when the frame
+ * does not record its size (error statuses of that function are always < -0x2000). */
 int64_t acc_snappy_uncompressed_length(const void *src, int64_t src_len, int64_t *err_offset);
 int64_t acc_zstd_frame_content_size(const void *src, int64_t src_len, int64_t *err_offset);
 
