@@ -59,16 +59,20 @@ __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p)
 // Short runs (the common case on LZ sequences) take one predicated byte move per lane; long runs use
 // 16-byte stores with the source re-aligned through funnel shifts.
 // NOTE: no __restrict__ on src -- match copies read bytes this kernel wrote earlier, which must not go
-// through the non-coherent (ld.global.nc) path.
+// through the non-coherent (ld.global.nc) path.  kCg = true reads through L2 only (ld.global.cg), for
+// sources that were produced with atomics (which bypass L1).
+template <bool kCg = false>
 __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int64_t n, int lane)
 {
+    auto ld8 = [](const uint8_t *p) -> uint8_t { return kCg ? __ldcg(p) : *p; };
+    auto ld32 = [](const uint32_t *p) -> uint32_t { return kCg ? __ldcg(p) : *p; };
     if (n <= 64) {
-        if (lane < n) dst[lane] = src[lane];
-        if (lane + 32 < n) dst[lane + 32] = src[lane + 32];
+        if (lane < n) dst[lane] = ld8(src + lane);
+        if (lane + 32 < n) dst[lane + 32] = ld8(src + lane + 32);
         return;
     }
     int head = (int) ((16 - ((uintptr_t) dst & 15)) & 15);
-    if (lane < head) dst[lane] = src[lane];
+    if (lane < head) dst[lane] = ld8(src + lane);
     dst += head; src += head; n -= head;
     int64_t nvec = n >> 4;
     uintptr_t sa = (uintptr_t) src;
@@ -77,8 +81,8 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int6
     uint4 *d16 = (uint4 *) dst;
     for (int64_t v = lane; v < nvec; v += 32) {
         const uint32_t *s = s32 + v * 4;
-        uint32_t w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];
-        uint32_t w4 = sh ? s[4] : 0;
+        uint32_t w0 = ld32(s), w1 = ld32(s + 1), w2 = ld32(s + 2), w3 = ld32(s + 3);
+        uint32_t w4 = sh ? ld32(s + 4) : 0;
         uint4 o;
         o.x = __funnelshift_r(w0, w1, sh * 8);
         o.y = __funnelshift_r(w1, w2, sh * 8);
@@ -88,7 +92,7 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int6
     }
     int64_t done = nvec << 4;
     int tail = (int) (n - done);
-    if (lane < tail) dst[done + lane] = src[done + lane];
+    if (lane < tail) dst[done + lane] = ld8(src + done + lane);
 }
 
 // Warp-cooperative LZ77 match copy inside the output buffer with forward byte-copy semantics:

@@ -129,3 +129,64 @@ def test_java_shaped_zstd_decompressor(oracle):
     with pytest.raises(acb.MalformedInputException, match="Not enough input bytes"):
         d.decompress(bytes([40, 181, 47, 253, 32, 0, 1, 0]), 0, 8, bytearray(1024), 0, 1024)
     assert d.decompress(z, 0, len(z), bytearray(0), 0, 0) == 0            # ZstdFrameDecompressor.java:143-145
+
+
+def test_compress_roundtrips_through_reference_decoders(engine, oracle, refnative, sample_blocks, synthetic_cases, pieces):
+    rng = np.random.default_rng(21)
+    blocks = synthetic_cases + sample_blocks + [bytes(range(256))[:n] for n in range(1, 256, 7)]
+    blocks += [b"\x07" * 168890, np.concatenate(pieces[:9]).tobytes()[:1000000], _read("incompressible"),
+               bytes(rng.integers(0, 256, 200000, dtype=np.uint8)) + b"abcabcabd" * 40, bytes(rng.integers(97, 101, 300000, dtype=np.uint8))]
+    src, so, sl = _pack(blocks, pad=3)
+    L = acb.lib()
+    caps = np.array([L.acc_zstd_compress_bound(len(b)) for b in blocks], dtype=np.int64)
+    do = np.concatenate([[0], np.cumsum(caps + 32)[:-1]]).astype(np.int64)
+    dst = np.full(int((caps + 32).sum()), 0x5A, dtype=np.uint8)
+    out_len, status = engine.run_host(acb.OP_ZSTD_COMPRESS, src, so, sl, dst, do, caps)
+    tin = tout = tref = 0
+    for i, blk in enumerate(blocks):
+        assert status[i] == 0, (i, hex(status[i]))
+        c = dst[do[i]:do[i] + out_len[i]].tobytes()
+        assert 0 < len(c) <= caps[i], (i, len(c), caps[i])
+        assert (dst[do[i] + caps[i]:do[i] + caps[i] + 32] == 0x5A).all()
+        r, off, ref = oracle.decompress_raw("zstd", c, len(blk))                 # Java decoder rules, exact-size output
+        assert r == len(blk), (i, len(blk), r, (-r) >> 8 if r < 0 else 0, off)
+        assert ref[:r].tobytes() == blk
+        assert refnative.decompress("zstd", c, len(blk)) == blk                 # independent verify decompressor (libzstd 1.5.6)
+        import ctypes as C
+        buf = np.frombuffer(c, dtype=np.uint8)
+        assert oracle.lib.orc_zstd_decompressed_size(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(c), None) == len(blk)
+        tin += len(blk); tout += len(c); tref += len(oracle.compress("zstd", blk))
+    print(f"zstd: gpu ratio {tout / tin:.4f}, reference (java port) ratio {tref / tin:.4f}")
+    # too-small output -> argument error
+    out_len, status = engine.run_host(acb.OP_ZSTD_COMPRESS, src, so[20:21], sl[20:21], dst, do[:1], caps[20:21] - 1)
+    assert status[0] & 0xFF == 3
+
+
+def test_gpu_zstd_roundtrip_batch_property(engine, pieces):
+    """compress -> decompress of 2048 x 128 KiB blocks on the GPU returns the input (whole-buffer compare)."""
+    blocks = benchdata.cut_blocks(pieces, 128 * 1024)
+    blocks = (blocks * (2048 // len(blocks) + 1))[:2048]
+    src, so, sl = benchdata.pack(blocks)
+    L = acb.lib()
+    caps = np.array([L.acc_zstd_compress_bound(int(n)) for n in sl], dtype=np.int64)
+    do = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.int64)
+    comp = np.zeros(int(caps.sum()), dtype=np.uint8)
+    clen, st = engine.run_host(acb.OP_ZSTD_COMPRESS, src, so, sl, comp, do, caps)
+    assert (st == 0).all()
+    back = np.zeros_like(src)
+    dlen, st = engine.run_host(acb.OP_ZSTD_DECOMPRESS, comp, do, clen, back, so, sl)
+    assert (st == 0).all() and (dlen == sl).all()
+    assert np.array_equal(back, src)
+    print(f"zstd gpu ratio on 128 KiB blocks: {clen.sum() / sl.sum():.4f}")
+
+
+def test_java_shaped_zstd_compressor(oracle):
+    c, d = acb.ZstdCudaCompressor(), acb.ZstdCudaDecompressor()
+    assert [c.maxCompressedLength(n) for n in (0, 65536, 131072, 131073)] == [64, 65824, 131584, 131585]   # AbstractTestZstd.java:140-147
+    data = _read("with-checksum") * 3
+    out = bytearray(c.maxCompressedLength(len(data)) + 5)
+    n = c.compress(data, 0, len(data), out, 5, len(out) - 5)
+    assert oracle.decompress("zstd", bytes(out[5:5 + n]), len(data)) == data
+    back = bytearray(len(data))
+    assert d.decompress(out, 5, n, back, 0, len(back)) == len(data) and bytes(back) == data
+    assert d.getDecompressedSize(out, 5, n) == len(data)
