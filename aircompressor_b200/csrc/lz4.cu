@@ -12,6 +12,10 @@ namespace {
 constexpr int kMinMatch = 4;
 constexpr int kLastLiterals = 5;
 
+// floor(65536 / d) + 1: (m * kRcp16[d]) >> 16 == m / d for m < 32
+__constant__ uint32_t kRcp16[32] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
+                                    4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
+
 // ------------------------------------------------------------------------------------------------
 // Decode: one warp per block.  All lanes walk the token stream redundantly (broadcast loads), the
 // literal and match copies are spread over the 32 lanes.
@@ -30,7 +34,40 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
         return;
     }
 
+    // ---- fast path ------------------------------------------------------------------------------
+    // Most sequences have no length-extension bytes (literal length < 15, match length < 19), i.e. they
+    // produce at most 32 bytes.  For those, every lane resolves the source of ONE output byte directly
+    // (a literal from the input, an older output byte, or -- when the match overlaps this sequence's own
+    // literals / itself -- the literal it ultimately repeats) and the whole sequence is a single
+    // load + store per lane.  The bounds below are exactly the conditions under which the Java decoder
+    // takes its normal (non-final) path (Lz4RawDecompressor.java:82,168), so results are identical.
+    const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
     while (ip < in_len) {
+        if (small && ip + 25 <= in_len && op + 44 <= out_cap) {
+            const uint32_t tk = __ldg(in + ip);
+            const uint32_t fll = tk >> 4, fml = tk & 15;
+            if (fll != 15 && fml != 15) {
+                const uint32_t lit0 = (uint32_t) ip + 1;
+                const uint32_t foff = (uint32_t) __ldg(in + lit0 + fll) | ((uint32_t) __ldg(in + lit0 + fll + 1) << 8);
+                if (foff == 0 || foff > (uint32_t) op + fll) LZ4_FAIL((int64_t) lit0 + fll + 2, ACC_R_OFFSET_OUTSIDE);
+                const uint32_t total = fll + fml + kMinMatch;
+                if ((uint32_t) lane < total) {
+                    uint8_t v;
+                    if ((uint32_t) lane < fll) v = __ldg(in + lit0 + lane);
+                    else {
+                        uint32_t m = (uint32_t) lane - fll;
+                        if (m >= foff) m -= foff * ((m * kRcp16[foff]) >> 16);   // m % offset (offset < 18 here)
+                        const int32_t rel = (int32_t) fll - (int32_t) foff + (int32_t) m;   // relative to op
+                        v = rel >= 0 ? __ldg(in + lit0 + rel) : out[op + rel];
+                    }
+                    out[op + lane] = v;
+                }
+                __syncwarp();
+                ip = lit0 + fll + 2;
+                op += total;
+                continue;
+            }
+        }
         const uint32_t token = in[ip++];
         uint32_t ll = token >> 4;
         if (ll == 15) {
@@ -187,14 +224,15 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                     if (cand >= 0 && cand < p && p - cand <= 65535 && ld_u32_unaligned(in + cand) == (uint32_t) v) hit = true;
                 }
                 __syncwarp();
-                // insert after the lookups so that lanes see the table as of the batch start
-                if (p <= match_find_limit) {
+                // Insert after the lookups (lanes see the table as of the batch start), and only positions up to
+                // the first match: a position behind the match end would otherwise be looked up again by the next
+                // batch and find itself instead of its older candidate.
+                unsigned hits = __ballot_sync(kFull, hit);
+                const int first_hit = hits ? __ffs(hits) - 1 : 31;
+                if (p <= match_find_limit && lane <= first_hit) {
                     uint64_t v = ld_u64_unaligned(in + p);
                     table[lz4_hash5(v)] = (int32_t) p;
                 }
-                // also let a lane match a slightly older position inside the same batch: checked via the
-                // table on the next batch only -- kept simple here.
-                unsigned hits = __ballot_sync(kFull, hit);
                 if (hits == 0) {
                     pos += 32;
                     continue;

@@ -226,9 +226,10 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
                     if (cand != 0xffff && cand < p && ld_u32_unaligned(base + cand) == cur) hit = true;
                 }
                 __syncwarp();
-                // position 65535 cannot be stored (0xffff = empty); it is never a match start anyway
-                if (p <= fast_limit && p < 0xffff) table[snappy_hash(cur)] = (uint16_t) p;
+                // insert only up to the first match (see lz4.cu); position 65535 cannot be stored (0xffff = empty)
                 unsigned hits = __ballot_sync(kFull, hit);
+                const int first_hit = hits ? __ffs(hits) - 1 : 31;
+                if (p <= fast_limit && p < 0xffff && lane <= first_hit) table[snappy_hash(cur)] = (uint16_t) p;
                 if (hits == 0) { pos += 32; continue; }
                 const int first = __ffs(hits) - 1;
                 const int64_t mpos = pos + first;

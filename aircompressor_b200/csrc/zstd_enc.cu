@@ -356,8 +356,9 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                             if (cand < (uint32_t) p && ld_u32_unaligned(blk + cand) == cur) hit = true;
                         }
                         __syncwarp();
-                        if (p < probe_limit) sm.u.hash[(cur * 2654435761u) >> (32 - kHashLog)] = (uint32_t) p;
                         const unsigned hits = __ballot_sync(kFull, hit);
+                        const int first_hit = hits ? __ffs(hits) - 1 : 31;
+                        if (p < probe_limit && lane <= first_hit) sm.u.hash[(cur * 2654435761u) >> (32 - kHashLog)] = (uint32_t) p;   // see lz4.cu
                         if (hits == 0) { pos += 32; continue; }
                         const int first = __ffs(hits) - 1;
                         int mpos = pos + first;

@@ -31,6 +31,14 @@ CODEC_OPS = {
 }
 
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -126,7 +134,7 @@ def run_reference(args, rank, world):
         return
     from oracle.pyoracle import Oracle
     orc = Oracle()
-    threads = orc.max_threads()
+    threads = host_threads()
     n_sample = min(args.blocks, args.ref_blocks)
     wl = build_workload(args.codec, args.block_kib, n_sample, orc, threads)
     op = CODEC_OPS[(args.codec, args.op)]
@@ -210,7 +218,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     orc = Oracle()
-    threads = orc.max_threads()
+    threads = host_threads()
     eng = acb.BatchEngine(local_rank)
     if args.ctas_per_sm:
         eng.set_tuning(0, args.ctas_per_sm)
