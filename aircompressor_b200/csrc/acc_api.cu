@@ -26,6 +26,7 @@ struct acc_ctx {
     int64_t last_offset = 0;
     int64_t launches = 0;
     int tuning_ctas_per_sm = 0;
+    int tuning_decoder = 0;   // 0 = default, 1 = warp-per-block (v1), 3 = shared-memory window (v3)
 };
 
 static thread_local int32_t t_init_error = 0;
@@ -102,6 +103,8 @@ int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
 {
     if (!c) return 0;
     if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
+    if (key == 1) { int prev = c->tuning_decoder; c->tuning_decoder = value; return prev; }
+    if (key == 2) { extern int g_tpb_max_ctas; int prev = g_tpb_max_ctas; g_tpb_max_ctas = value; return prev; }
     return 0;
 }
 
@@ -178,7 +181,7 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
     b.work_counter = next_counter(c, st);
     switch (op) {
         case ACC_OP_LZ4_COMPRESS: acc_launch_lz4_compress(b, c->sm_count, st); break;
-        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
+        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, c->tuning_decoder, st); break;
         case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
         case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;

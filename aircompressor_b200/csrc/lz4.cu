@@ -6,125 +6,13 @@
 // block the Java decoder accepts (round-trip parity, the reference's own contract:
 // AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
+#include "lz4_decode_v1.cuh"
 
 namespace {
 
-constexpr int kMinMatch = 4;
-constexpr int kLastLiterals = 5;
+using namespace lz4v1;
 
-// floor(65536 / d) + 1: (m * kRcp16[d]) >> 16 == m / d for m < 32
-__constant__ uint32_t kRcp16[32] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
-                                    4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
-
-// ------------------------------------------------------------------------------------------------
-// Decode: one warp per block.  All lanes walk the token stream redundantly (broadcast loads), the
-// literal and match copies are spread over the 32 lanes.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in, int64_t in_len, uint8_t *out, int64_t out_cap,
-                                                 int64_t *out_len, int32_t *status, int lane)
-{
-#define LZ4_FAIL(off, reason) do { if (lane == 0) { *out_len = (off); *status = ACC_STATUS(ACC_E_MALFORMED, reason); } return; } while (0)
-    const int64_t fast_output_limit = out_cap - 8;
-    int64_t ip = 0, op = 0;
-
-    if (in_len == 0) LZ4_FAIL(0, ACC_R_INPUT_EMPTY);
-    if (out_cap == 0) {
-        if (in_len == 1 && in[0] == 0) { if (lane == 0) { *out_len = 0; *status = 0; } return; }
-        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_LZ4_ZERO_CAPACITY); }
-        return;
-    }
-
-    // ---- fast path ------------------------------------------------------------------------------
-    // Most sequences have no length-extension bytes (literal length < 15, match length < 19), i.e. they
-    // produce at most 32 bytes.  For those, every lane resolves the source of ONE output byte directly
-    // (a literal from the input, an older output byte, or -- when the match overlaps this sequence's own
-    // literals / itself -- the literal it ultimately repeats) and the whole sequence is a single
-    // load + store per lane.  The bounds below are exactly the conditions under which the Java decoder
-    // takes its normal (non-final) path (Lz4RawDecompressor.java:82,168), so results are identical.
-    const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
-    while (ip < in_len) {
-        if (small && ip + 25 <= in_len && op + 44 <= out_cap) {
-            const uint32_t tk = __ldg(in + ip);
-            const uint32_t fll = tk >> 4, fml = tk & 15;
-            if (fll != 15 && fml != 15) {
-                const uint32_t lit0 = (uint32_t) ip + 1;
-                const uint32_t foff = (uint32_t) __ldg(in + lit0 + fll) | ((uint32_t) __ldg(in + lit0 + fll + 1) << 8);
-                if (foff == 0 || foff > (uint32_t) op + fll) LZ4_FAIL((int64_t) lit0 + fll + 2, ACC_R_OFFSET_OUTSIDE);
-                const uint32_t total = fll + fml + kMinMatch;
-                if ((uint32_t) lane < total) {
-                    uint8_t v;
-                    if ((uint32_t) lane < fll) v = __ldg(in + lit0 + lane);
-                    else {
-                        uint32_t m = (uint32_t) lane - fll;
-                        if (m >= foff) m -= foff * ((m * kRcp16[foff]) >> 16);   // m % offset (offset < 18 here)
-                        const int32_t rel = (int32_t) fll - (int32_t) foff + (int32_t) m;   // relative to op
-                        v = rel >= 0 ? __ldg(in + lit0 + rel) : out[op + rel];
-                    }
-                    out[op + lane] = v;
-                }
-                __syncwarp();
-                ip = lit0 + fll + 2;
-                op += total;
-                continue;
-            }
-        }
-        const uint32_t token = in[ip++];
-        uint32_t ll = token >> 4;
-        if (ll == 15) {
-            if (ip >= in_len) LZ4_FAIL(ip, ACC_R_NONE);
-            uint32_t v;
-            do {
-                v = in[ip++];
-                ll += v;  // 32-bit wrap like the Java int
-            }
-            while (v == 255 && ip < in_len - 15);
-        }
-        if ((int32_t) ll < 0) LZ4_FAIL(ip, ACC_R_NONE);
-
-        const int64_t lit_end = ip + (int64_t) ll;
-        const int64_t lit_out_limit = op + (int64_t) ll;
-        if (lit_out_limit > fast_output_limit - kMinMatch || lit_end > in_len - (2 + 1 + kLastLiterals)) {
-            if (lit_out_limit > out_cap) LZ4_FAIL(ip, ACC_R_LAST_LITERAL_OUTSIDE);
-            if (lit_end != in_len) LZ4_FAIL(ip, ACC_R_ALL_INPUT_CONSUMED);
-            warp_copy(out + op, in + ip, ll, lane);
-            op += ll;
-            break;
-        }
-        warp_copy(out + op, in + ip, ll, lane);
-        op = lit_out_limit;
-        ip = lit_end;
-
-        const uint32_t offset = ld_u16le(in + ip);
-        ip += 2;
-        if ((int64_t) offset > op || offset == 0) LZ4_FAIL(ip, ACC_R_OFFSET_OUTSIDE);
-
-        uint32_t ml = token & 15;
-        if (ml == 15) {
-            uint32_t v;
-            do {
-                if (ip > in_len - kLastLiterals) LZ4_FAIL(ip, ACC_R_NONE);
-                v = in[ip++];
-                ml += v;
-            }
-            while (v == 255);
-        }
-        ml += kMinMatch;
-        if ((int32_t) ml < 0) LZ4_FAIL(ip, ACC_R_NONE);
-
-        const int64_t match_out_limit = op + (int64_t) ml;
-        if (match_out_limit > fast_output_limit - kMinMatch) {
-            if (match_out_limit > out_cap - kLastLiterals) LZ4_FAIL(ip, ACC_R_LAST5_LITERALS);
-        }
-        __syncwarp();
-        warp_match_copy(out + op, offset, ml, lane);
-        __syncwarp();
-        op = match_out_limit;
-    }
-    if (lane == 0) { *out_len = op; *status = 0; }
-#undef LZ4_FAIL
-}
-
-__global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
+__global__ void __launch_bounds__(256, 8) lz4_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
     for (;;) {
@@ -288,8 +176,13 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
 
 }  // namespace
 
-void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
+void acc_launch_lz4_decompress_v3(const AccBatch &b, int sm_count, cudaStream_t st);    // lz4_v3.cu
+void acc_launch_lz4_decompress_tpb(const AccBatch &b, int sm_count, cudaStream_t st);   // lz4_tpb.cu
+
+void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
+    if (version == 3) { acc_launch_lz4_decompress_v3(b, sm_count, st); return; }
+    if (version == 2) { acc_launch_lz4_decompress_tpb(b, sm_count, st); return; }
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t warps_needed = b.n;
     int64_t ctas = (warps_needed + 7) / 8;

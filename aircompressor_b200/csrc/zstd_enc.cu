@@ -20,15 +20,17 @@
 //      walk the three state chains, then all threads OR their sequences' bits at prefix-sum offsets;
 //   5. block assembly, raw-block fallback when the gain is below the reference's threshold.
 #include "zstd_common.cuh"
+#include "zstd_fse_enc.cuh"
 #include "xxh64_device.cuh"
 
 namespace {
 using namespace zs;
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
+constexpr int kNQ = kThreads / 32;                         // sub-ranges of a block, one per warp
 constexpr int kHashLog = 13;
-constexpr int kMaxSeqQ = kMaxBlock / 4 / 4 + 16;         // sequences per quarter (min match 4)
-constexpr int kMaxSeq = 4 * kMaxSeqQ;
+constexpr int kMaxSeqQ = kMaxBlock / kNQ / 4 + 16;       // sequences per sub-range (min match 4)
+constexpr int kMaxSeq = kNQ * kMaxSeqQ;
 constexpr int kStreamStage = 48 * 1024;                  // staging bytes per Huffman stream (32768 symbols x 11 bits)
 constexpr int kSeqStage = kMaxBlock + 1024;              // staging bytes for the sequence bitstream
 constexpr int64_t kScratchPerCta = (int64_t) kMaxSeq * 8 + (kMaxBlock + 64) + (int64_t) 3 * kMaxSeq * 2 + 4 * kStreamStage + kSeqStage + 256;
@@ -43,8 +45,9 @@ struct EncSmem {
     uint16_t ll_next[64], ml_next[64], of_next[32];
     int32_t ll_dnb[36], ll_dfs[36], ml_dnb[53], ml_dfs[53], of_dnb[29], of_dfs[29];
     int32_t scan[kThreads + 1];
-    int32_t qcount[4], qtrail[4], qbase[5];
+    int32_t qcount[kNQ], qtrail[kNQ], qbase[kNQ + 1];
     int32_t v[24];   // broadcast slots
+    uint8_t wbuf[264];   // serialized Huffman table description (header byte + weights)
 };
 
 enum { V_NSEQ = 0, V_LASTLIT, V_NLIT, V_LITMODE, V_MAXSYM, V_HUFBITS, V_HTABLE_BYTES, V_STREAM_BYTES0, V_STREAM_BYTES1, V_STREAM_BYTES2,
@@ -262,12 +265,12 @@ template <bool kCg = false>
 __device__ __forceinline__ void block_copy(uint8_t *dst, const uint8_t *src, int64_t n)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t per = ((n + 3) / 4 + 15) & ~15LL;
+    int64_t per = ((n + kNQ - 1) / kNQ + 15) & ~15LL;
     int64_t a = per * warp, b = a + per < n ? a + per : n;
     if (a < b) warp_copy<kCg>(dst + a, src + a, b - a, lane);
 }
 
-__global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uint8_t *scratch_base)
+__global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uint8_t *scratch_base, const int64_t *frame_hashes)
 {
     __shared__ EncSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -319,11 +322,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
             }
             op = 5 + (single_segment ? 0 : 1) + (cs_desc == 0 ? (single_segment ? 1 : 0) : (cs_desc == 1 ? 2 : 4));
         }
-        // frame checksum: lanes 0-3 of warp 3 hash the input while nothing else needs them (before the first barrier of the block loop)
-        if (warp == 3) {
-            uint64_t h = xxh64_group4(in, lane < 4 ? in_len : 0, 0, lane & 3, 0xFu << (lane & ~3));
-            if (lane == 0) sm.v[V_CHECKSUM] = (int32_t) (uint32_t) h;
-        }
+        // frame checksum: XXH64 of the whole input, computed for the batch by xxh64_kernel before this kernel
+        if (tid == 0) sm.v[V_CHECKSUM] = (int32_t) (uint32_t) (uint64_t) frame_hashes[idx];
 
         int64_t block_start = 0;
         bool last_block;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 for (int i = tid; i < (1 << kHashLog); i += kThreads) sm.u.hash[i] = 0xFFFFFFFFu;
                 __syncthreads();
                 {
-                    const int q = ((bl + 3) / 4 + 31) & ~31;
+                    const int q = ((bl + kNQ - 1) / kNQ + 31) & ~31;
                     const int qs = min(q * warp, bl), qe = min(qs + q, bl);
                     uint64_t *my = seqs + (int64_t) warp * kMaxSeqQ;
                     int count = 0, anchor = qs, pos = qs;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 // ================= 2. concatenate the quarter lists, gather literals =================
                 if (tid == 0) {
                     int carry = 0, base = 0;
-                    for (int w = 0; w < 4; w++) {
+                    for (int w = 0; w < kNQ; w++) {
                         sm.qbase[w] = base;
                         if (sm.qcount[w] > 0) {
                             uint64_t *first = seqs + (int64_t) w * kMaxSeqQ;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         else carry += sm.qtrail[w];
                         base += sm.qcount[w];
                     }
-                    sm.qbase[4] = base;
+                    sm.qbase[kNQ] = base;
                     sm.v[V_NSEQ] = base;
                     sm.v[V_LASTLIT] = carry;
                 }
@@ -403,7 +403,9 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 __syncthreads();
                 const int nseq = sm.v[V_NSEQ], last_lit = sm.v[V_LASTLIT];
                 auto seq_at = [&](int i) -> uint64_t {
-                    int w = (i >= sm.qbase[1]) + (i >= sm.qbase[2]) + (i >= sm.qbase[3]);
+                    int w = 0;
+#pragma unroll
+                    for (int k = 1; k < kNQ; k++) w += (i >= sm.qbase[k]);
                     return seqs[(int64_t) w * kMaxSeqQ + (i - sm.qbase[w])];
                 };
                 const int chunk = (nseq + kThreads - 1) / kThreads;
@@ -433,7 +435,6 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         for (int s = 0; s <= max_symbol; s++) largest = max(largest, (int) sm.hist[s]);
                         if (largest == nlit) mode = 1;
                         else if (largest <= (nlit >> 7) + 4) mode = 0;
-                        else if (max_symbol > 128) mode = 0;   // direct 4-bit weights hold at most 128 entries; FSE-compressed weights: not yet
                         else {
                             // optimalNumberOfBits(11, nlit, maxSymbol) (HuffmanCompressionTable.java:41-58)
                             int r = 11, v1 = highbit((uint32_t) (nlit - 1)) - 1;
@@ -443,8 +444,24 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                             if (r < 5) r = 5;
                             if (r > 12) r = 12;
                             hbits = huf_build(sm, max_symbol, r);
-                            table_bytes = 1 + (max_symbol + 1) / 2;
-                            mode = 2;
+                            // table description (HuffmanCompressionTable.write :202-263): FSE-compressed weights when that is
+                            // smaller than the direct 4-bit form (and mandatory above 128 entries, which the direct form cannot hold)
+                            uint8_t weights[256];
+                            for (int s2 = 0; s2 < max_symbol; s2++) weights[s2] = sm.hbits[s2] ? (uint8_t) (hbits + 1 - sm.hbits[s2]) : 0;
+                            const int fsz = fse_compress_weights(sm.wbuf + 1, 250, weights, max_symbol);
+                            if (fsz > 1 && fsz < max_symbol / 2 && fsz < 128) {
+                                sm.wbuf[0] = (uint8_t) fsz;
+                                table_bytes = 1 + fsz;
+                                mode = 2;
+                            }
+                            else if (max_symbol <= 128) {
+                                sm.wbuf[0] = (uint8_t) (127 + max_symbol);
+                                weights[max_symbol] = 0;
+                                for (int i = 0; i < max_symbol; i += 2) sm.wbuf[1 + i / 2] = (uint8_t) ((weights[i] << 4) + weights[i + 1]);
+                                table_bytes = 1 + (max_symbol + 1) / 2;
+                                mode = 2;
+                            }
+                            else mode = 0;
                         }
                     }
                     sm.v[V_NLIT] = nlit; sm.v[V_LITMODE] = mode; sm.v[V_MAXSYM] = max_symbol; sm.v[V_HUFBITS] = hbits; sm.v[V_HTABLE_BYTES] = table_bytes;
@@ -586,15 +603,9 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                             if (lit_header == 3) { uint32_t h = type | ((single_stream ? 0 : 1) << 2) | (nlit << 4) | (total << 14); o[0] = h; o[1] = h >> 8; o[2] = h >> 16; }
                             else if (lit_header == 4) { uint32_t h = type | (2 << 2) | (nlit << 4) | ((uint32_t) total << 18); o[0] = h; o[1] = h >> 8; o[2] = h >> 16; o[3] = h >> 24; }
                             else { uint32_t h = (uint32_t) type | (3u << 2) | ((uint32_t) nlit << 4) | ((uint32_t) total << 22); o[0] = h; o[1] = h >> 8; o[2] = h >> 16; o[3] = h >> 24; o[4] = (uint8_t) ((uint32_t) total >> 10); }
-                            // Huffman table: direct weights (HuffmanCompressionTable.write :240-262)
+                            // Huffman table description prepared in shared memory during planning
                             uint8_t *t = o + lit_header;
-                            const int max_symbol = sm.v[V_MAXSYM], hb = sm.v[V_HUFBITS];
-                            t[0] = (uint8_t) (127 + max_symbol);
-                            for (int i = 0; i < max_symbol; i += 2) {
-                                int w0 = sm.hbits[i] ? hb + 1 - sm.hbits[i] : 0;
-                                int w1 = (i + 1 < max_symbol && sm.hbits[i + 1]) ? hb + 1 - sm.hbits[i + 1] : 0;
-                                t[1 + i / 2] = (uint8_t) ((w0 << 4) + w1);
-                            }
+                            for (int i = 0; i < sm.v[V_HTABLE_BYTES]; i++) t[i] = sm.wbuf[i];
                             if (!single_stream) {
                                 uint8_t *j = t + sm.v[V_HTABLE_BYTES];
                                 j[0] = (uint8_t) sb0; j[1] = (uint8_t) (sb0 >> 8); j[2] = (uint8_t) sb1; j[3] = (uint8_t) (sb1 >> 8); j[4] = (uint8_t) sb2; j[5] = (uint8_t) (sb2 >> 8);
@@ -667,7 +678,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
 
 static int64_t zstd_enc_grid(int sm_count) { return (int64_t) sm_count * 5; }
 
-int64_t acc_zstd_enc_scratch_bytes(int sm_count) { return zstd_enc_grid(sm_count) * kScratchPerCta; }
+int64_t acc_zstd_enc_scratch_bytes(int sm_count, int64_t n) { return zstd_enc_grid(sm_count) * kScratchPerCta + n * 8 + 256; }
 
 void acc_launch_zstd_compress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes)
 {
@@ -676,5 +687,11 @@ void acc_launch_zstd_compress(const AccBatch &b, int sm_count, cudaStream_t st, 
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     (void) scratch_bytes;
-    zstd_compress_kernel<<<(unsigned) ctas, kThreads, 0, st>>>(b, (uint8_t *) scratch);
+    // pass 1: XXH64 of every input (frame checksum, ZstdFrameCompressor.java:123-134) at HBM speed
+    int64_t *hashes = reinterpret_cast<int64_t *>((uint8_t *) scratch + zstd_enc_grid(sm_count) * kScratchPerCta);
+    AccBatch hb = b;
+    hb.out_len = hashes;
+    hb.status = nullptr;
+    acc_launch_xxh64(hb, 0, sm_count, st);
+    zstd_compress_kernel<<<(unsigned) ctas, kThreads, 0, st>>>(b, (uint8_t *) scratch, hashes);
 }

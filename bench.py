@@ -27,7 +27,7 @@ import benchdata  # noqa: E402
 GiB = float(1 << 30)
 CODEC_OPS = {
     ("lz4", "decompress"): 1, ("lz4", "compress"): 0, ("snappy", "decompress"): 3, ("snappy", "compress"): 2,
-    ("zstd", "decompress"): 5, ("zstd", "compress"): 4,
+    ("zstd", "decompress"): 5, ("zstd", "compress"): 4, ("xxh64", "hash"): 6,
 }
 
 
@@ -102,6 +102,9 @@ def build_workload(codec, block_kib, n_blocks, orc, threads):
     label, pieces = benchdata.load_pieces()
     blocks = benchdata.cut_blocks(pieces, block_kib * 1024)
     raw, raw_off, raw_len = benchdata.pack(blocks)
+    if codec == "xxh64":
+        return {"label": label, "distinct": len(blocks), "raw": raw, "raw_off": raw_off, "raw_len": raw_len,
+                "comp": raw, "comp_off": raw_off, "comp_len": raw_len, "n": n_blocks}
     bound = orc.max_compressed_length(codec, int(raw_len.max()))
     caps = np.full(len(blocks), bound, dtype=np.int64)
     coff = (np.arange(len(blocks), dtype=np.int64) * bound)
@@ -179,7 +182,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd"])
+    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd", "xxh64"])
     ap.add_argument("--op", default="decompress", choices=["compress", "decompress"])
     ap.add_argument("--block-kib", type=int, default=0, help="default 64 (lz4/snappy) or 128 (zstd)")
     ap.add_argument("--blocks", type=int, default=0, help="default: 4 GiB of uncompressed data per GPU")
@@ -188,8 +191,12 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short per-codec side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--decoder", type=int, default=0, help="LZ4 decoder kernel: 1 warp-per-block, 3 shared-memory window, 0 library default")
+    ap.add_argument("--tpb-ctas", type=int, default=0, help="thread-per-block decoder: number of 128-thread CTAs")
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): no e2e, no cpu baseline, warm-up as given")
     args = ap.parse_args()
+    if args.codec == "xxh64":
+        args.op = "hash"
     if args.block_kib == 0:
         args.block_kib = 128 if args.codec == "zstd" else 64
     if args.blocks == 0:
@@ -222,6 +229,10 @@ def main():
     eng = acb.BatchEngine(local_rank)
     if args.ctas_per_sm:
         eng.set_tuning(0, args.ctas_per_sm)
+    if args.decoder:
+        eng.set_tuning(1, args.decoder)
+    if args.tpb_ctas:
+        eng.set_tuning(2, args.tpb_ctas)
     op = CODEC_OPS[(args.codec, args.op)]
     n = args.blocks
 
@@ -237,7 +248,13 @@ def main():
 
     raw_d, raw_off_d, raw_len_d, raw_off_h, raw_len_h = to_dev_tiled(wl["raw"], wl["raw_off"], wl["raw_len"])
     unc_bytes = int(raw_len_h.sum())
-    if args.op == "decompress":
+    if args.op == "hash":
+        src_d, src_off_d, src_len_d, src_off_h, src_len_h = raw_d, raw_off_d, raw_len_d, raw_off_h, raw_len_h
+        dst_d = torch.zeros(16, dtype=torch.uint8, device=dev)
+        dst_off_d = torch.zeros(n, dtype=torch.int64, device=dev)
+        dst_cap_d = torch.zeros(n, dtype=torch.int64, device=dev)
+        comp_bytes = 0
+    elif args.op == "decompress":
         src_d, src_off_d, src_len_d, src_off_h, src_len_h = to_dev_tiled(wl["comp"], wl["comp_off"], wl["comp_len"])
         dst_d = torch.zeros_like(raw_d)
         dst_off_d, dst_cap_d = raw_off_d, raw_len_d
@@ -273,7 +290,14 @@ def main():
     torch.cuda.synchronize()
     # verification (untimed): all blocks OK and bytes identical to the originals
     assert int((status_d != 0).sum()) == 0, "kernel reported errors"
-    if args.op == "decompress":
+    if args.op == "hash":
+        d = wl["distinct"]
+        got = out_len_d[:d].cpu().numpy()
+        for i in range(0, d, max(1, d // 16)):
+            blk = wl["raw"][wl["raw_off"][i]:wl["raw_off"][i] + wl["raw_len"][i]]
+            assert int(got[i]) & 0xFFFFFFFFFFFFFFFF == orc.xxh64(blk.tobytes(), 0), "xxh64 mismatch"
+        comp_bytes = 0
+    elif args.op == "decompress":
         assert bool((out_len_d == raw_len_d).all())
         end = int(raw_off_h[-1] + raw_len_h[-1])
         assert torch.equal(dst_d[:end], raw_d[:end]), "decompressed batch differs from the original bytes"
@@ -305,8 +329,8 @@ def main():
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) ----------------
     e2e = None
     try:
-        if args.profile:
-            raise RuntimeError("skipped (--profile)")
+        if args.profile or args.op == "hash":
+            raise RuntimeError("skipped")
         h_src = torch.empty(src_d.numel(), dtype=torch.uint8, pin_memory=True)
         h_src.copy_(src_d)
         h_dst = torch.empty(dst_d.numel(), dtype=torch.uint8, pin_memory=True)
@@ -345,7 +369,9 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(f"{args.codec}_{args.op}")
+            t = json.load(open(prof)).get(f"{args.codec}_{args.op}")
+            # ncu capture of this kernel on the same workload shape; scaled to this run's batch size
+            traffic = t["dram_bytes_per_launch"] * n / t["captured_with_blocks"] if t else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -355,7 +381,7 @@ def main():
                 "kernel_ms_avg": avg_kernel_ms, "kernel_ms_min": float(np.min(kernel_ms))}
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.op != "hash":
         ns = min(n, args.ref_blocks)
         _, _, _, soff, slen = tile_index(wl["comp_off"] if args.op == "decompress" else wl["raw_off"],
                                          wl["comp_len"] if args.op == "decompress" else wl["raw_len"], ns)

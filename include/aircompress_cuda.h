@@ -141,7 +141,8 @@ int32_t acc_zstd_decompress_batch(acc_ctx *, const void *, const int64_t *, cons
 int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, int64_t *, int64_t, int32_t, int64_t);
 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
- * key 0: resident CTAs per SM for the decode kernels; other keys are ignored. */
+ * key 0: resident CTAs per SM for the warp-per-block decode kernels; key 1: LZ4 decoder (1 = warp per block,
+ * 3 = shared-memory window); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);
 
 #ifdef __cplusplus

@@ -41,8 +41,16 @@ def _gpu_decompress(engine, codec, streams, caps, guard=0):
     return dst, do, out_len, status
 
 
+@pytest.fixture(params=[1, 2, 3], ids=["warp-per-block", "thread-per-block", "smem-window"])
+def decoder(request, engine):
+    """runs the decode tests against both LZ4 decoder kernels (tuning key 1)"""
+    engine.set_tuning(1, request.param)
+    yield request.param
+    engine.set_tuning(1, 0)
+
+
 @pytest.mark.parametrize("codec", ["lz4", "snappy"])
-def test_decompress_matches_oracle_on_corpus(engine, oracle, refnative, codec, sample_blocks, synthetic_cases):
+def test_decompress_matches_oracle_on_corpus(engine, oracle, refnative, codec, sample_blocks, synthetic_cases, decoder):
     blocks = [b for b in synthetic_cases + sample_blocks]
     streams, caps, want = [], [], []
     for i, blk in enumerate(blocks):
@@ -63,7 +71,7 @@ def test_decompress_matches_oracle_on_corpus(engine, oracle, refnative, codec, s
 
 
 @pytest.mark.parametrize("codec", ["lz4", "snappy"])
-def test_decompress_error_parity_on_corrupt_streams(engine, oracle, codec, sample_blocks):
+def test_decompress_error_parity_on_corrupt_streams(engine, oracle, codec, sample_blocks, decoder):
     """Bit flips, truncations and wrong capacities: GPU status word and offset == oracle's."""
     rng = np.random.default_rng(99)
     streams, caps = [], []
@@ -105,7 +113,7 @@ def test_decompress_error_parity_on_corrupt_streams(engine, oracle, codec, sampl
     assert n_bad > 10
 
 
-def test_lz4_overflow_streams(engine, oracle):
+def test_lz4_overflow_streams(engine, oracle, decoder):
     # T/lz4/AbstractTestLz4.java:28-67 (shortened: the 9 MB run is what overflows the Java int)
     n = (2**31 - 1) // 255 + 1
     lit = bytes([0xF0]) + b"\xff" * n + bytes([1]) + bytes(20)
@@ -143,7 +151,7 @@ def test_compress_roundtrips_through_reference_decoders(engine, oracle, refnativ
 
 
 @pytest.mark.parametrize("codec", ["lz4", "snappy"])
-def test_gpu_roundtrip_full_batch_property(engine, codec, pieces):
+def test_gpu_roundtrip_full_batch_property(engine, codec, pieces, decoder):
     """Size-independent property at bench scale: compress -> decompress of every 64 KiB block of the
     corpus sample tiled to 4096 blocks returns the input (checked by comparing whole buffers)."""
     blocks = benchdata.cut_blocks(pieces, 64 * 1024)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one `ncu --set full` capture per kernel on the bench workload (1 GPU); reports land in gpurun_out/
+prof() { # name codec op kernel-regex blocks
+  ncu --set full --clock-control none --import-source on -k regex:$4 -s 3 -c 1 -o gpurun_out/prof_r1_$1 \
+      python bench.py --profile --codec $2 --op $3 --steps 1 --warmup 3 --blocks $5 > gpurun_out/ncu_$1.log 2>&1
+  tail -1 gpurun_out/ncu_$1.log | cut -c1-120
+}
+prof lz4_decompress lz4 decompress lz4_decompress_kernel 65536
+prof lz4_compress lz4 compress lz4_compress_kernel 16384
+prof snappy_decompress snappy decompress snappy_decompress_kernel 32768
+prof snappy_compress snappy compress snappy_compress_kernel 16384
+prof zstd_decompress zstd decompress zstd_decompress_kernel 8192
+prof zstd_compress zstd compress zstd_compress_kernel 8192
+prof xxh64 xxh64 hash xxh64_kernel 65536
+ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
