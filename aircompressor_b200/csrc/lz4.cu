@@ -12,7 +12,7 @@ namespace {
 
 using namespace lz4v1;
 
-__global__ void __launch_bounds__(256, 8) lz4_decompress_kernel(AccBatch b)
+__global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
     for (;;) {

@@ -97,7 +97,7 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
 #undef SN_FAIL
 }
 
-__global__ void __launch_bounds__(256, 8) snappy_decompress_kernel(AccBatch b)
+__global__ void __launch_bounds__(256) snappy_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
     for (;;) {
