@@ -55,7 +55,53 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
     const int64_t fast_output_limit = out_cap - 8;
     int64_t ip = 0, op = 0;
 
+    const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
     while (ip < in_len) {
+        // ---- fast path: [literal of <= 27 bytes] + [one 1- or 2-byte-offset copy], parsed from one coalesced 32-byte load.
+        // Every output byte is resolved independently (a literal byte of this step, or older output through the periodic
+        // source formula), so the step is one load and one store per lane and 32-byte chunk.  The bounds make the elements
+        // valid under SnappyRawDecompressor.java:89-216; anything else goes to the element-by-element path below.
+        if (small && ip + 32 <= in_len) {
+            const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
+            const uint32_t vb = __ldg(in + ipw + lane);
+            const uint32_t t0 = __shfl_sync(kFull, vb, 0);
+            uint32_t L = 0, p = 0;
+            bool ok = true;
+            if ((t0 & 3) == 0) {
+                const uint32_t n = t0 >> 2;
+                if (n <= 26) { L = n + 1; p = 1 + L; } else ok = false;
+            }
+            if (ok) {
+                const uint32_t tag = __shfl_sync(kFull, vb, p);
+                const uint32_t b1 = __shfl_sync(kFull, vb, (p + 1) & 31), b2 = __shfl_sync(kFull, vb, (p + 2) & 31);
+                const uint32_t kind = tag & 3;
+                uint32_t clen = 0, coff = 1, adv = p;
+                if (kind == 1) { clen = 4 + ((tag >> 2) & 7); coff = ((tag >> 5) << 8) | b1; adv = p + 2; }
+                else if (kind == 2) { clen = (tag >> 2) + 1; coff = b1 | (b2 << 8); adv = p + 3; }
+                else if (L == 0) ok = false;          // long literal / 4-byte-offset copy first: slow path
+                const uint32_t total = L + clen;
+                if (ok && coff != 0 && coff <= opw + L && (uint64_t) opw + total <= (uint64_t) out_cap) {
+                    for (uint32_t c = 0; c < total; c += 32) {
+                        const uint32_t j = c + lane;
+                        int32_t rel = (int32_t) j;     // position relative to op of the byte to copy (literal: itself, from the window)
+                        if (j >= L) {
+                            uint32_t m = j - L;
+                            if (m >= coff) m = m % coff;
+                            rel = (int32_t) L - (int32_t) coff + (int32_t) m;
+                        }
+                        uint32_t v = __shfl_sync(kFull, vb, (rel + 1) & 31);
+                        if (j < total) {
+                            if (rel < 0) v = out[(int64_t) opw + rel];
+                            out[opw + j] = (uint8_t) v;
+                        }
+                    }
+                    __syncwarp();
+                    ip = ipw + adv;
+                    op = opw + total;
+                    continue;
+                }
+            }
+        }
         const uint32_t opc = in[ip++];
         const uint32_t entry = snappy_op_entry(opc);
         const int trailer_bytes = (int) (entry >> 11);
