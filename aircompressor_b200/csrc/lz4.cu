@@ -63,12 +63,18 @@ __device__ __forceinline__ int64_t lz4_emit_literal_run(uint8_t *out, int64_t op
     return op + ll;
 }
 
+// TableT = uint16_t serves blocks of at most 64 KiB (positions fit 16 bits, 8 KiB of table per warp -> twice the resident
+// warps); TableT = int32_t serves larger blocks.  Each instantiation skips the blocks that belong to the other one.
+template <typename TableT>
 __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccBatch b)
 {
-    extern __shared__ int32_t lz4_tables[];  // kLz4WarpsPerCta x kLz4Table positions
+    extern __shared__ __align__(16) uint8_t lz4_tables_raw[];  // kLz4WarpsPerCta x kLz4Table positions
+    TableT *lz4_tables = reinterpret_cast<TableT *>(lz4_tables_raw);
+    constexpr bool kSmallBlocks = sizeof(TableT) == 2;
+    constexpr TableT kEmpty = (TableT) -1;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    int32_t *table = lz4_tables + warp * kLz4Table;
+    TableT *table = lz4_tables + warp * kLz4Table;
 
     for (;;) {
         unsigned int idx = 0;
@@ -81,6 +87,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
         uint8_t *out = b.dst + b.dst_off[idx];
         const int64_t out_cap = b.dst_cap[idx];
 
+        if ((in_len <= 65536) != kSmallBlocks) continue;   // handled by the other instantiation
         if (in_len > 0x7E000000) {
             if (lane == 0) { b.out_len[idx] = 0; b.status[idx] = ACC_STATUS(ACC_E_ARGUMENT, ACC_R_MAX_INPUT_EXCEEDED); }
             continue;
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
             continue;
         }
 
-        for (int i = lane; i < kLz4Table; i += 32) table[i] = -1;
+        for (int i = lane; i < kLz4Table; i += 32) table[i] = kEmpty;
         __syncwarp();
 
         int64_t op = 0;
@@ -108,7 +115,8 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                 if (p <= match_find_limit) {
                     uint64_t v = ld_u64_unaligned(in + p);
                     uint32_t h = lz4_hash5(v);
-                    cand = table[h];
+                    const TableT tv = table[h];
+                    cand = tv == kEmpty ? -1 : (int32_t) tv;
                     if (cand >= 0 && cand < p && p - cand <= 65535 && ld_u32_unaligned(in + cand) == (uint32_t) v) hit = true;
                 }
                 __syncwarp();
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                 const int first_hit = hits ? __ffs(hits) - 1 : 31;
                 if (p <= match_find_limit && lane <= first_hit) {
                     uint64_t v = ld_u64_unaligned(in + p);
-                    table[lz4_hash5(v)] = (int32_t) p;
+                    table[lz4_hash5(v)] = (TableT) p;
                 }
                 if (hits == 0) {
                     pos += 32;
@@ -192,13 +200,25 @@ void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm,
     lz4_decompress_kernel<<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
-void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st)
+void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter)
 {
     int64_t ctas = (b.n + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
-    int64_t max_ctas = (int64_t) sm_count * 3;  // 64 KiB of tables per CTA -> 3 CTAs per SM
-    if (ctas > max_ctas) ctas = max_ctas;
-    if (ctas < 1) ctas = 1;
-    const int smem = kLz4WarpsPerCta * kLz4Table * (int) sizeof(int32_t);
-    cudaFuncSetAttribute(lz4_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // per device, cheap
-    lz4_compress_kernel<<<(unsigned) ctas, kLz4WarpsPerCta * 32, smem, st>>>(b);
+    // blocks <= 64 KiB: 16-bit tables, 32 KiB per CTA -> 7 CTAs (28 warps) per SM
+    {
+        const int smem = kLz4WarpsPerCta * kLz4Table * (int) sizeof(uint16_t);
+        cudaFuncSetAttribute(lz4_compress_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int64_t g = ctas < (int64_t) sm_count * 7 ? ctas : (int64_t) sm_count * 7;
+        if (g < 1) g = 1;
+        lz4_compress_kernel<uint16_t><<<(unsigned) g, kLz4WarpsPerCta * 32, smem, st>>>(b);
+    }
+    // larger blocks: 32-bit tables (64 KiB per CTA -> 3 CTAs per SM); exits immediately when there are none
+    {
+        AccBatch b2 = b;
+        b2.work_counter = second_counter;
+        const int smem = kLz4WarpsPerCta * kLz4Table * (int) sizeof(int32_t);
+        cudaFuncSetAttribute(lz4_compress_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int64_t g = ctas < (int64_t) sm_count * 3 ? ctas : (int64_t) sm_count * 3;
+        if (g < 1) g = 1;
+        lz4_compress_kernel<int32_t><<<(unsigned) g, kLz4WarpsPerCta * 32, smem, st>>>(b2);
+    }
 }

@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(256) snappy_decompress_kernel(AccBatch b)
 
 // ------------------------------------------------------------------------------------------------
 // Encode: one warp per input; independent 64 KiB fragments (SnappyRawCompressor.java:37-38,93) are
-// walked in order with a 16,384 x uint16 position table in shared memory (same shape as the
+// walked in order with an 8,192 x uint16 position table in shared memory (half the size of the
 // reference's short[16384], SnappyRawCompressor.java:43-45,348-361) that is reset per fragment.
 // 32 positions are probed per step with the reference's hash (value * 0x1e35a7bd >>> shift,
 // SnappyRawCompressor.java:368-371); ballot selects the first match, a second ballot extends it.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSnTableBits = 14;
+constexpr int kSnTableBits = 13;   // 8192 x uint16 per warp (the reference uses 16384): 16 KiB per warp, twice the resident warps
 constexpr int kSnTable = 1 << kSnTableBits;
-constexpr int kSnWarpsPerCta = 2;
+constexpr int kSnWarpsPerCta = 4;
 constexpr int kSnFragment = 1 << 16;
 
 __device__ __forceinline__ uint32_t snappy_hash(uint32_t v) { return (v * 0x1e35a7bdu) >> (32 - kSnTableBits); }
