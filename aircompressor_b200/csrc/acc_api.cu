@@ -2,6 +2,7 @@
 //
 // There is deliberately no CPU code path for any codec in this file: every compress / decompress /
 // hash request becomes a kernel launch, and when no GPU is usable acc_init() fails.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,11 @@ struct acc_ctx {
     int64_t launches = 0;
     int tuning_ctas_per_sm = 0;
     int tuning_decoder = 0;   // 0 = default, 1 = warp-per-block (v1), 3 = shared-memory window (v3)
+    int tuning_pipeline = 0;  // host-pointer batches: 0 = auto, 1 = never split, k > 1 = split into k chunks
+    // copy streams + events of the pipelined host-pointer path (created on first use)
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {}, ev_start = nullptr;
 };
 
 static thread_local int32_t t_init_error = 0;
@@ -75,6 +81,10 @@ void acc_destroy(acc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    for (int i = 0; i < acc_ctx::kMaxChunks; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
     cudaFree(c->counters); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_idx); cudaFree(c->d_scratch);
     if (c->h_idx) cudaFreeHost(c->h_idx);
     delete c;
@@ -104,6 +114,7 @@ int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
     if (!c) return 0;
     if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
     if (key == 1) { int prev = c->tuning_decoder; c->tuning_decoder = value; return prev; }
+    if (key == 3) { int prev = c->tuning_pipeline; c->tuning_pipeline = value; return prev; }
     if (key == 2) { extern int g_tpb_max_ctas; int prev = g_tpb_max_ctas; g_tpb_max_ctas = value; return prev; }
     return 0;
 }
@@ -201,6 +212,75 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
     return 0;
 }
 
+// ---- pipelined host-pointer path ---------------------------------------------------------------------
+// A large batch is cut into runs of consecutive blocks; run k's input upload (copy stream 1), its kernel (the
+// caller's stream) and its output download (copy stream 2) overlap with the neighbours' so that the call costs about
+// max(H2D, kernels, D2H) instead of their sum. Runs hold >= 8192 blocks: the decoders give one warp per block, and a
+// launch with fewer blocks than resident warps is bound by single-block latency, not throughput.
+static int pipeline_chunks(acc_ctx *c, int64_t n, int64_t bytes, const int64_t *src_off)
+{
+    if (c->tuning_pipeline == 1) return 1;
+    int64_t k = c->tuning_pipeline > 1 ? c->tuning_pipeline : std::min<int64_t>(n / 8192, bytes / (32 << 20));
+    if (k > acc_ctx::kMaxChunks) k = acc_ctx::kMaxChunks;
+    if (k > n) k = n;
+    if (k < 2) return 1;
+    for (int64_t i = 1; i < n; i++) if (src_off[i] < src_off[i - 1]) return 1;   // runs must cover ascending input ranges
+    if (!c->s_h2d) {
+        if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return 1; }
+        for (int i = 0; i < acc_ctx::kMaxChunks; i++) {
+            if (cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return 1; }
+        }
+    }
+    return (int) k;
+}
+
+static int32_t batch_host_pipelined(acc_ctx *c, int32_t op, const void *src_base, const int64_t *src_off, const int64_t *src_len,
+                                    void *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t n, cudaStream_t st,
+                                    uint64_t seed, int chunks, int64_t src_lo, int64_t src_pad, int64_t dst_lo, int64_t dst_pad, bool has_dst)
+{
+    int64_t *h = c->h_idx;
+    int32_t rc = 0;
+#define PIPE_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess && rc == 0) rc = -ACC_STATUS(ACC_E_CUDA, (int) e_); } while (0)
+    PIPE_TRY(cudaEventRecord(c->ev_start, st));                 // order after whatever the caller queued on st
+    PIPE_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_start, 0));
+    PIPE_TRY(cudaMemcpyAsync(c->d_idx, h, (size_t) (4 * n * 8), cudaMemcpyHostToDevice, c->s_h2d));
+    for (int k = 0; k < chunks && rc == 0; k++) {
+        const int64_t b0 = n * k / chunks, b1 = n * (k + 1) / chunks, m = b1 - b0;
+        int64_t lo = src_off[b0], hi = lo;
+        for (int64_t i = b0; i < b1; i++) hi = std::max(hi, src_off[i] + src_len[i]);
+        if (hi > lo)
+            PIPE_TRY(cudaMemcpyAsync(c->d_src + src_pad + (lo - src_lo), (const uint8_t *) src_base + lo, (size_t) (hi - lo),
+                                     cudaMemcpyHostToDevice, c->s_h2d));
+        PIPE_TRY(cudaEventRecord(c->ev_in[k], c->s_h2d));
+        PIPE_TRY(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        AccBatch b{c->d_src, c->d_idx + b0, c->d_idx + n + b0, c->d_dst, c->d_idx + 2 * n + b0, c->d_idx + 3 * n + b0,
+                   c->d_idx + 4 * n + b0, (int32_t *) (c->d_idx + 5 * n) + b0, m, nullptr};
+        if (rc == 0) rc = enqueue(c, op, b, st, seed);
+        PIPE_TRY(cudaEventRecord(c->ev_done[k], st));
+        PIPE_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
+        if (has_dst && rc == 0) {
+            int64_t run_lo = dst_off[b0], run_hi = dst_off[b0] + dst_cap[b0];
+            for (int64_t i = b0 + 1; i <= b1; i++) {
+                if (i < b1 && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
+                if (run_hi > run_lo)
+                    PIPE_TRY(cudaMemcpyAsync((uint8_t *) dst_base + run_lo, c->d_dst + dst_pad + (run_lo - dst_lo), (size_t) (run_hi - run_lo),
+                                             cudaMemcpyDeviceToHost, c->s_d2h));
+                if (i < b1) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
+            }
+        }
+    }
+    if (rc == 0) PIPE_TRY(cudaMemcpyAsync(h + 4 * n, c->d_idx + 4 * n, (size_t) (n * 8 + n * 4), cudaMemcpyDeviceToHost, c->s_d2h));
+    // always drain all three streams, also on failure, before the staging buffers can be reused
+    PIPE_TRY(cudaStreamSynchronize(c->s_h2d));
+    PIPE_TRY(cudaStreamSynchronize(st));
+    PIPE_TRY(cudaStreamSynchronize(c->s_d2h));
+#undef PIPE_TRY
+    return rc;
+}
+
 static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const int64_t *src_off, const int64_t *src_len,
                           void *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int32_t *status,
                           int64_t n, int32_t flags, int64_t stream, uint64_t seed)
@@ -249,6 +329,15 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
         h[2 * n + i] = has_dst ? dst_off[i] - dst_lo + dst_pad : 0;
         h[3 * n + i] = has_dst ? dst_cap[i] : 0;
     }
+    const int chunks = pipeline_chunks(c, n, src_bytes + dst_bytes, src_off);
+    if (chunks > 1) {
+        int32_t r = batch_host_pipelined(c, op, src_base, src_off, src_len, dst_base, dst_off, dst_cap, n, st, seed, chunks,
+                                         src_lo, src_pad, dst_lo, dst_pad, has_dst);
+        if (r != 0) return r;
+        memcpy(out_len, h + 4 * n, (size_t) (n * 8));
+        if (status) memcpy(status, h + 5 * n, (size_t) (n * 4));
+        return 0;
+    }
     CU_TRY(cudaMemcpyAsync(c->d_idx, h, (size_t) (4 * n * 8), cudaMemcpyHostToDevice, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
     if (src_bytes > 0)
         CU_TRY(cudaMemcpyAsync(c->d_src + src_pad, (const uint8_t *) src_base + src_lo, (size_t) src_bytes, cudaMemcpyHostToDevice, st),
@@ -258,8 +347,7 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
     int32_t r = enqueue(c, op, b, st, seed);
     if (r != 0) return r;
     CU_TRY(cudaMemcpyAsync(h + 4 * n, c->d_idx + 4 * n, (size_t) (n * 8 + n * 4), cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
-    const bool is_compress = op == ACC_OP_LZ4_COMPRESS || op == ACC_OP_SNAPPY_COMPRESS || op == ACC_OP_ZSTD_COMPRESS;
-    if (has_dst && dst_bytes > 0 && !(is_compress && n == 1)) {
+    if (has_dst && dst_bytes > 0 && n > 1) {
         // copy back every block's [dst_off, dst_off + dst_cap) window and nothing outside of them: windows that
         // touch are merged into one transfer (a gap-free batch is a single D2H copy)
         int64_t run_lo = dst_off[0], run_hi = dst_off[0] + dst_cap[0];
@@ -272,8 +360,9 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
         }
     }
     CU_TRY(cudaStreamSynchronize(st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
-    if (has_dst && dst_bytes > 0 && is_compress && n == 1) {
-        // single compress call: copy back only the bytes produced
+    if (has_dst && dst_bytes > 0 && n == 1) {
+        // single-block call (the Java-shaped entry points): copy back only the bytes produced, so that the caller's
+        // buffer beyond the returned length stays untouched like it does with the reference codecs
         int64_t produced = h[4 * n];
         int32_t stt = ((int32_t *) (h + 5 * n))[0];
         if (stt == 0 && produced > 0) {

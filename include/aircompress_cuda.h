@@ -124,7 +124,12 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
  * dst_base + dst_off[i].  `stream` is a CUstream/cudaStream_t handle (0 = the context's own non-blocking
  * stream; pass 1 (cudaStreamLegacy) or 2 (cudaStreamPerThread) to target CUDA's default streams);
  * with ACC_F_DEVICE_POINTERS the work is only enqueued.  Without it the library copies host->device,
- * runs, copies results back and synchronises before returning.
+ * runs, copies results back and synchronises before returning; large batches are cut into runs of consecutive
+ * blocks whose upload, kernel and download overlap (see acc_set_tuning key 3).
+ * Output contract: bytes [0, out_len[i]) of window i are the result; the rest of the window
+ * [out_len[i], dst_cap[i]) is unspecified after a host-pointer batch of more than one block (whole windows are
+ * copied back so that touching windows merge into one transfer); bytes outside every window are never written.
+ * The single-block entry points above write only the bytes they return, like the reference codecs.
  */
 int32_t acc_batch(acc_ctx *ctx, int32_t op,
                   const void *src_base, const int64_t *src_off, const int64_t *src_len,
@@ -142,7 +147,9 @@ int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t 
 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
  * key 0: resident CTAs per SM for the warp-per-block decode kernels; key 1: LZ4 decoder (1 = warp per block,
- * 3 = shared-memory window); other keys are ignored. */
+ * 2 = thread per block, 3 = shared-memory window); key 2: CTA count of the thread-per-block decoder;
+ * key 3: host-pointer batches, 1 = never split, k > 1 = split into k overlapped upload/kernel/download runs
+ * (default: automatic for batches of >= 16384 blocks and >= 64 MiB); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);
 
 #ifdef __cplusplus

@@ -171,6 +171,49 @@ def test_gpu_roundtrip_full_batch_property(engine, codec, pieces, decoder):
     assert np.array_equal(back, src)
 
 
+@pytest.mark.parametrize("codec", ["lz4", "snappy"])
+def test_pipelined_host_path_equals_single_pass(engine, oracle, codec, pieces):
+    """acc_batch with host pointers cuts large batches into overlapped upload/kernel/download runs (tuning key 3).
+    The split must not change a byte: lengths, statuses (some blocks are corrupted on purpose), outputs and the
+    guard bytes between output windows are compared between 1 run and 5 runs, for both directions."""
+    blocks = benchdata.cut_blocks(pieces, 16 * 1024)[:333]
+    src, so, sl = benchdata.pack(blocks)
+    bound = getattr(acb.lib(), f"acc_{codec}_compress_bound")
+    caps = np.array([bound(int(n)) + 7 for n in sl], dtype=np.int64)
+    do = np.concatenate([[0], np.cumsum(caps + 5)[:-1]]).astype(np.int64)     # 5 guard bytes after every window
+    results = []
+    for chunks in (1, 5):
+        engine.set_tuning(3, chunks)
+        try:
+            comp = np.full(int(do[-1] + caps[-1] + 5), 0x5A, dtype=np.uint8)
+            clen, st = engine.run_host(OPS[codec][0], src, so, sl, comp, do, caps)
+            assert (st == 0).all()
+            bad = comp.copy()
+            for i in range(0, len(blocks), 17):       # corrupt every 17th stream: statuses must survive the split too
+                bad[do[i] + clen[i] // 2] ^= 0xFF
+                bad[do[i] + clen[i] // 2 + 1] ^= 0x81
+            back = np.full(len(src) + 64, 0xC3, dtype=np.uint8)
+            dlen, dst = engine.run_host(OPS[codec][1], bad, do, clen, back, so, sl)
+            results.append((comp, clen, back, dlen, dst))
+        finally:
+            engine.set_tuning(3, 0)
+    a, b = results
+    for k in (1, 3, 4):                       # clen, dlen (error offsets included), statuses
+        assert np.array_equal(a[k], b[k])
+    for i in range(len(blocks)):              # produced bytes; the rest of a window is unspecified (aircompress_cuda.h)
+        assert np.array_equal(a[0][do[i]:do[i] + a[1][i]], b[0][do[i]:do[i] + b[1][i]])
+        if a[4][i] == 0:
+            assert np.array_equal(a[2][so[i]:so[i] + a[3][i]], b[2][so[i]:so[i] + b[3][i]])
+    comp, clen, back, dlen, dst = b
+    for i in range(len(blocks)):
+        if i % 17:
+            assert dst[i] == 0 and dlen[i] == sl[i] and bytes(back[so[i]:so[i] + sl[i]]) == blocks[i]
+    assert (dst[::17] != 0).sum() > 0
+    assert (back[len(src):] == 0xC3).all()
+    for i in range(len(blocks)):
+        assert (comp[do[i] + caps[i]:do[i] + caps[i] + 5] == 0x5A).all()
+
+
 def test_java_shaped_single_block_api():
     c, d = acb.Lz4CudaCompressor(), acb.Lz4CudaDecompressor()
     data = b"XXXXabcdefgh abcdefgh abcdefgh abcdefgh abcdefgh abcdefgh ABC" * 50

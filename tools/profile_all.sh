@@ -11,5 +11,5 @@ prof snappy_decompress snappy decompress snappy_decompress_kernel 32768
 prof snappy_compress snappy compress snappy_compress_kernel 16384
 prof zstd_decompress zstd decompress zstd_decompress_kernel 8192
 prof zstd_compress zstd compress zstd_compress_kernel 8192
-prof xxh64 xxh64 hash xxh64_kernel 65536
+prof xxh64 xxh64 decompress xxh64 65536
 ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
