@@ -12,6 +12,7 @@ namespace {
 
 using namespace lz4v1;
 
+template <int kFast>
 __global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
@@ -20,8 +21,8 @@ __global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
         if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if ((int64_t) idx >= b.n) break;
-        lz4_decode_block(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
-                         b.out_len + idx, b.status + idx, lane);
+        lz4_decode_block<kFast>(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
+                                b.out_len + idx, b.status + idx, lane);
     }
 }
 
@@ -197,7 +198,9 @@ void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm,
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    lz4_decompress_kernel<<<(unsigned) ctas, 256, 0, st>>>(b);
+    if (version == 4) lz4_decompress_kernel<1><<<(unsigned) ctas, 256, 0, st>>>(b);        // one sequence per step (first round-1 kernel)
+    else if (version == 5) lz4_decompress_kernel<2><<<(unsigned) ctas, 256, 0, st>>>(b);   // multi-sequence steps only
+    else lz4_decompress_kernel<3><<<(unsigned) ctas, 256, 0, st>>>(b);                     // + medium steps
 }
 
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter)

@@ -17,6 +17,9 @@ static __constant__ uint32_t kRcp16[32] = {0, 65537, 32769, 21846, 16385, 13108,
 // Decode: one warp per block.  All lanes walk the token stream redundantly (broadcast loads), the
 // literal and match copies are spread over the 32 lanes.
 // ------------------------------------------------------------------------------------------------
+// kFast selects the fast path: 1 = one sequence per step, 2 = up to three sequences per step,
+// 3 = 2 + medium steps for sequences with one length-extension byte.
+template <int kFast = 3>
 __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in, int64_t in_len, uint8_t *out, int64_t out_cap,
                                                  int64_t *out_len, int32_t *status, int lane)
 {
@@ -39,8 +42,123 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
     // load + store per lane.  The bounds below are exactly the conditions under which the Java decoder
     // takes its normal (non-final) path (Lz4RawDecompressor.java:82,168), so results are identical.
     const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
+    // multi-sequence steps run while ip <= ip_lim && op <= op_lim (-1: never)
+    const int32_t ip_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) in_len - 40 : -1;
+    const int32_t op_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) out_cap - 44 : -1;
+    // per-lane base pointers, made opaque so that the compiler keeps the 64-bit sums in registers instead of re-adding
+    // kernel parameters in the loop
+    const uint8_t *in_lane = in + lane;
+    uint8_t *out_lane = out + lane;
+    const uint8_t *out_rd = out;
+    asm volatile("" : "+l"(in_lane));
+    asm volatile("" : "+l"(out_lane));
+    asm volatile("" : "+l"(out_rd));
+    uint8_t *out_rd_w = const_cast<uint8_t *>(out_rd);
     while (ip < in_len) {
-        if (small && ip + 32 <= in_len && op + 44 <= out_cap) {
+        if (kFast >= 2) {
+            // ---- multi-sequence steps: up to three short sequences (no length-extension bytes) whose tokens, literals
+            // and offsets all lie in the 32-byte input window at ip and whose output fits the 32 lanes.
+            // Every lane first treats ITS byte as a token and works out what a sequence starting there would be
+            // (literal length, output bytes, offset); the warp then follows the chain 0 -> next token -> next token
+            // with three shuffles per sequence, and every lane resolves the source of one output byte: a literal of the
+            // window, older output (one global load), or a byte another lane produces in this same step (taken by
+            // shuffle once that lane has it; the dependency always points to a lower lane, so the loop ends after at
+            // most three rounds, usually zero).
+            // Bounds: every sequence ends <= ip + 32 <= in_len - 8 and <= op + 32 <= out_cap - 12, which are the Java
+            // decoder's conditions for the normal (non-final) path (Lz4RawDecompressor.java:82,168); a sequence with a bad
+            // offset is left for the next step to report (it then is sequence 0), so error offsets are unchanged.
+            uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
+            while ((int32_t) ipw <= ip_lim && (int32_t) opw <= op_lim) {
+                const uint32_t vb = __ldg(in_lane + ipw);
+                const uint32_t ll_l = vb >> 4, ml_l = vb & 15;
+                const uint32_t o_lo = __shfl_sync(kFull, vb, lane + 1 + ll_l);
+                const uint32_t o_hi = __shfl_sync(kFull, vb, lane + 2 + ll_l);
+                const uint32_t off_l = o_hi * 256 + o_lo;
+                // output bytes of a sequence starting at this lane; 63 (never fits) when it needs the general path
+                const uint32_t n_l = (vb < 0xF0 && ml_l != 15 && (uint32_t) lane + ll_l <= 29) ? ll_l + ml_l + kMinMatch : 63u;
+                const uint32_t e0 = __shfl_sync(kFull, n_l, 0);
+                if (e0 > 32) {
+                    if (kFast != 3) break;
+                    // ---- medium step: ONE sequence whose literal and/or match length carries a single extension byte
+                    // (lengths up to 269 / 273; 92 % of the sequences the steps above cannot take).  Anything unusual --
+                    // a second extension byte, the end-of-block rules, a bad offset, a match overlapping itself at a
+                    // distance below 32 -- leaves through `break` BEFORE ip/op move, and the general path below decodes
+                    // the sequence again from its token (and reports the error, if there is one).
+                    const uint32_t tok = __shfl_sync(kFull, vb, 0);
+                    uint32_t ll = tok >> 4, ml = tok & 15, pos = 1;
+                    if (ll == 15) {
+                        const uint32_t x = __shfl_sync(kFull, vb, 1);
+                        if (x == 255) break;
+                        ll += x;
+                        pos = 2;
+                    }
+                    const uint32_t lit_in = ipw + pos, lit_end = lit_in + ll;
+                    // Java's normal-path conditions (Lz4RawDecompressor.java:82): literals end 8 bytes before the input end
+                    // and 12 bytes before the output end
+                    if (lit_end + 8 > (uint32_t) in_len || opw + ll + 12 > (uint32_t) out_cap) break;
+                    const uint32_t off = (uint32_t) __ldg(in + lit_end) | ((uint32_t) __ldg(in + lit_end + 1) << 8);
+                    uint32_t used = pos + ll + 2;
+                    if (ml == 15) {
+                        const uint32_t x = __ldg(in + lit_end + 2);
+                        if (x == 255) break;
+                        ml += x;
+                        used++;
+                    }
+                    ml += kMinMatch;
+                    const uint32_t mop = opw + ll;                               // first output byte of the match
+                    if (off - 1 >= mop || (off < 32 && off < ml) || mop + ml + 12 > (uint32_t) out_cap) break;
+                    for (uint32_t i = lane; i < ll; i += 32) out_rd_w[opw + i] = __ldg(in + lit_in + i);
+                    __syncwarp();
+                    // 32 bytes per round; a round only reads bytes written at least 32 positions earlier, or (off >= ml,
+                    // single round) bytes in front of the match
+                    for (uint32_t base = 0; base < ml; base += 32) {
+                        const uint32_t i = base + lane;
+                        if (i < ml) out_rd_w[mop + i] = out_rd[mop + i - off];
+                        __syncwarp();
+                    }
+                    ipw += used;
+                    opw = mop + ml;
+                    continue;
+                }
+                const uint32_t ll0 = __shfl_sync(kFull, ll_l, 0), off0 = __shfl_sync(kFull, off_l, 0);
+                if (off0 - 1 >= opw + ll0) { ip = ipw; LZ4_FAIL((int64_t) ipw + ll0 + 3, ACC_R_OFFSET_OUTSIDE); }   // offset == 0 || offset > op
+                const uint32_t nx1 = 3 + ll0;                                   // <= 17: always inside the window
+                const uint32_t ll1 = __shfl_sync(kFull, ll_l, nx1), off1 = __shfl_sync(kFull, off_l, nx1);
+                const uint32_t e1 = e0 + __shfl_sync(kFull, n_l, nx1);
+                const bool v1 = e1 <= 32 && off1 - 1 < opw + e0 + ll1;
+                const uint32_t nx2 = nx1 + 3 + ll1;                             // <= 32 when v1
+                const uint32_t ll2 = __shfl_sync(kFull, ll_l, nx2), off2 = __shfl_sync(kFull, off_l, nx2);
+                const uint32_t e2 = e1 + __shfl_sync(kFull, n_l, nx2);
+                const bool v2 = v1 && nx2 < 32 && e2 <= 32 && off2 - 1 < opw + e1 + ll2;
+                const uint32_t e = v2 ? e2 : v1 ? e1 : e0;                      // output bytes of this step
+                const uint32_t nx = v2 ? nx2 + 3 + ll2 : v1 ? nx2 : nx1;        // input bytes of this step
+                // which sequence produces output byte `lane`
+                const bool k2 = v2 && (uint32_t) lane >= e1, k1 = v1 && (uint32_t) lane >= e0;
+                const uint32_t sk = k2 ? nx2 : k1 ? nx1 : 0u;                   // token position in the window
+                const uint32_t bk = k2 ? e1 : k1 ? e0 : 0u;                     // first output byte of the sequence
+                const uint32_t lk = k2 ? ll2 : k1 ? ll1 : ll0;
+                const uint32_t fk = k2 ? off2 : k1 ? off1 : off0;
+                const uint32_t t = (uint32_t) lane - bk;
+                const bool is_lit = t < lk;
+                uint32_t val = __shfl_sync(kFull, vb, sk + 1 + t);              // the literal, if it is one
+                int32_t m = (int32_t) t - (int32_t) lk;
+                if (!is_lit && (uint32_t) m >= fk) m -= (int32_t) (fk * (((uint32_t) m * kRcp16[fk]) >> 16));   // m mod offset (offset < 32 here)
+                const int32_t srel = (int32_t) (bk + lk) - (int32_t) fk + m;    // source, relative to op
+                uint32_t need = ((uint32_t) lane < e && !is_lit) ? 256u : 0u;
+                if (need && srel < 0) { val = out_rd[opw + (uint32_t) srel]; need = 0; }   // opw + srel >= 0 (offsets checked)
+                while (__any_sync(kFull, need)) {
+                    const uint32_t w = __shfl_sync(kFull, val | need, srel);
+                    if (need && !(w & 256u)) { val = w; need = 0; }
+                }
+                if ((uint32_t) lane < e) out_lane[opw] = (uint8_t) val;
+                __syncwarp();
+                ipw += nx;
+                opw += e;
+            }
+            ip = ipw;
+            op = opw;
+        }
+        if (kFast == 1 && small && ip + 32 <= in_len && op + 44 <= out_cap) {
             // one coalesced 32-byte load: lane l holds input byte ip + l (token, literals, offset all inside)
             const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
             const uint32_t vb = __ldg(in + ipw + lane);

@@ -41,7 +41,7 @@ def _gpu_decompress(engine, codec, streams, caps, guard=0):
     return dst, do, out_len, status
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["warp-per-block", "thread-per-block", "smem-window"])
+@pytest.fixture(params=[1, 2, 3, 4, 5], ids=["warp-per-block", "thread-per-block", "smem-window", "warp-single-seq", "warp-multi-seq"])
 def decoder(request, engine):
     """runs the decode tests against both LZ4 decoder kernels (tuning key 1)"""
     engine.set_tuning(1, request.param)
@@ -207,7 +207,7 @@ def test_pipelined_host_path_equals_single_pass(engine, oracle, codec, pieces):
     comp, clen, back, dlen, dst = b
     for i in range(len(blocks)):
         if i % 17:
-            assert dst[i] == 0 and dlen[i] == sl[i] and bytes(back[so[i]:so[i] + sl[i]]) == blocks[i]
+            assert dst[i] == 0 and dlen[i] == sl[i] and np.array_equal(back[so[i]:so[i] + sl[i]], blocks[i])
     assert (dst[::17] != 0).sum() > 0
     assert (back[len(src):] == 0xC3).all()
     for i in range(len(blocks)):
