@@ -194,7 +194,7 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
         case ACC_OP_LZ4_COMPRESS: acc_launch_lz4_compress(b, c->sm_count, st, next_counter(c, st)); c->launches++; break;
         case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, c->tuning_decoder, st); break;
         case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
-        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
+        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, c->tuning_decoder, st); break;
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
         case ACC_OP_ZSTD_COMPRESS:
         case ACC_OP_ZSTD_DECOMPRESS: {

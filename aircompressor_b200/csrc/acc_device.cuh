@@ -95,6 +95,10 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int6
     if (lane < tail) dst[done + lane] = ld8(src + done + lane);
 }
 
+// floor(65536 / d) + 1: (m * kRcp16[d]) >> 16 == m / d for m < 32
+static __constant__ uint32_t kRcp16[32] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
+                                    4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
+
 // Warp-cooperative LZ77 match copy inside the output buffer with forward byte-copy semantics:
 // dst[i] = dst[i - offset] for i in [0, len).  Callers __syncwarp() first so that earlier stores of
 // other lanes are visible.  offset >= 1.
@@ -128,7 +132,7 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, int64_t offset, in
 // kernel launchers implemented in the per-codec translation units
 void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st);
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter);
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st);
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st);
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st);
 void acc_launch_xxh64(const AccBatch &b, uint64_t seed, int sm_count, cudaStream_t st);
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes);

@@ -12,8 +12,9 @@ namespace {
 
 using namespace lz4v1;
 
-template <int kFast>
-__global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
+// kMinCtas: resident CTAs per SM the register allocation is bounded for (1 = compiler's choice)
+template <int kFast, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) lz4_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
     for (;;) {
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) lz4_decompress_kernel(AccBatch b)
         idx = __shfl_sync(kFull, idx, 0);
         if ((int64_t) idx >= b.n) break;
         lz4_decode_block<kFast>(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
-                                b.out_len + idx, b.status + idx, lane);
+                                b.out_len, b.status, idx, lane);
     }
 }
 
@@ -198,9 +199,13 @@ void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm,
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    if (version == 4) lz4_decompress_kernel<1><<<(unsigned) ctas, 256, 0, st>>>(b);        // one sequence per step (first round-1 kernel)
-    else if (version == 5) lz4_decompress_kernel<2><<<(unsigned) ctas, 256, 0, st>>>(b);   // multi-sequence steps only
-    else lz4_decompress_kernel<3><<<(unsigned) ctas, 256, 0, st>>>(b);                     // + medium steps
+    // default: multi-sequence + medium steps, registers bounded for 6 resident CTAs (40 registers, 48 warps per SM):
+    // 234 GiB/s vs 228 (5 CTAs), 200 (unbounded, 63 registers, 4 CTAs) and 234 (8 CTAs, more spills) on the bench batch
+    if (version == 4) lz4_decompress_kernel<1, 1><<<(unsigned) ctas, 256, 0, st>>>(b);        // one sequence per step (first round-1 kernel)
+    else if (version == 5) lz4_decompress_kernel<2, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // multi-sequence steps only
+    else if (version == 7) lz4_decompress_kernel<3, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else if (version == 8) lz4_decompress_kernel<3, 1><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else lz4_decompress_kernel<3, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter)

@@ -9,28 +9,33 @@ namespace lz4v1 {
 constexpr int kMinMatch = 4;
 constexpr int kLastLiterals = 5;
 
-// floor(65536 / d) + 1: (m * kRcp16[d]) >> 16 == m / d for m < 32
-static __constant__ uint32_t kRcp16[32] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370,
-                                    4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
-
 // ------------------------------------------------------------------------------------------------
 // Decode: one warp per block.  All lanes walk the token stream redundantly (broadcast loads), the
 // literal and match copies are spread over the 32 lanes.
 // ------------------------------------------------------------------------------------------------
-// kFast selects the fast path: 1 = one sequence per step, 2 = up to three sequences per step,
-// 3 = 2 + medium steps for sequences with one length-extension byte.
-template <int kFast = 3>
-__device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in, int64_t in_len, uint8_t *out, int64_t out_cap,
-                                                 int64_t *out_len, int32_t *status, int lane)
+// PosT is the type of the positions: int32_t for blocks below 2 GiB (the normal case: half the registers and
+// instructions), int64_t otherwise (no fast paths).  Sums that can leave the int32 range are formed in int64.
+template <int kFast, typename PosT>
+__device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_arg, const PosT in_len, uint8_t *out_arg, const PosT out_cap,
+                                                int64_t *out_len_base, int32_t *status_base, const uint32_t idx, const int lane)
 {
-#define LZ4_FAIL(off, reason) do { if (lane == 0) { *out_len = (off); *status = ACC_STATUS(ACC_E_MALFORMED, reason); } return; } while (0)
-    const int64_t fast_output_limit = out_cap - 8;
-    int64_t ip = 0, op = 0;
+#define LZ4_FAIL(off, reason) do { if (lane == 0) { out_len_base[idx] = (int64_t) (off); status_base[idx] = ACC_STATUS(ACC_E_MALFORMED, reason); } return; } while (0)
+    constexpr bool small = sizeof(PosT) == 4;
+    const PosT fast_output_limit = out_cap - 8;
+    PosT ip = 0, op = 0;
+    // base pointers made opaque, so that the compiler keeps these two 64-bit values in registers instead of re-adding
+    // kernel parameters (and holding the parts) inside the loops
+    const uint8_t *in = in_arg;
+    uint8_t *out = out_arg;
+    asm volatile("" : "+l"(in));
+    asm volatile("" : "+l"(out));
+    __builtin_assume(__isGlobal(in));    // laundering hides the address space: say it again, or the accesses become generic
+    __builtin_assume(__isGlobal(out));
 
     if (in_len == 0) LZ4_FAIL(0, ACC_R_INPUT_EMPTY);
     if (out_cap == 0) {
-        if (in_len == 1 && in[0] == 0) { if (lane == 0) { *out_len = 0; *status = 0; } return; }
-        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_LZ4_ZERO_CAPACITY); }
+        if (in_len == 1 && in[0] == 0) { if (lane == 0) { out_len_base[idx] = 0; status_base[idx] = 0; } return; }
+        if (lane == 0) { out_len_base[idx] = 0; status_base[idx] = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_LZ4_ZERO_CAPACITY); }
         return;
     }
 
@@ -41,21 +46,11 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
     // literals / itself -- the literal it ultimately repeats) and the whole sequence is a single
     // load + store per lane.  The bounds below are exactly the conditions under which the Java decoder
     // takes its normal (non-final) path (Lz4RawDecompressor.java:82,168), so results are identical.
-    const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
     // multi-sequence steps run while ip <= ip_lim && op <= op_lim (-1: never)
     const int32_t ip_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) in_len - 40 : -1;
     const int32_t op_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) out_cap - 44 : -1;
-    // per-lane base pointers, made opaque so that the compiler keeps the 64-bit sums in registers instead of re-adding
-    // kernel parameters in the loop
-    const uint8_t *in_lane = in + lane;
-    uint8_t *out_lane = out + lane;
-    const uint8_t *out_rd = out;
-    asm volatile("" : "+l"(in_lane));
-    asm volatile("" : "+l"(out_lane));
-    asm volatile("" : "+l"(out_rd));
-    uint8_t *out_rd_w = const_cast<uint8_t *>(out_rd);
     while (ip < in_len) {
-        if (kFast >= 2) {
+        if (small && kFast >= 2) {
             // ---- multi-sequence steps: up to three short sequences (no length-extension bytes) whose tokens, literals
             // and offsets all lie in the 32-byte input window at ip and whose output fits the 32 lanes.
             // Every lane first treats ITS byte as a token and works out what a sequence starting there would be
@@ -69,7 +64,7 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
             // offset is left for the next step to report (it then is sequence 0), so error offsets are unchanged.
             uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
             while ((int32_t) ipw <= ip_lim && (int32_t) opw <= op_lim) {
-                const uint32_t vb = __ldg(in_lane + ipw);
+                const uint32_t vb = __ldg(in + (ipw + (uint32_t) lane));
                 const uint32_t ll_l = vb >> 4, ml_l = vb & 15;
                 const uint32_t o_lo = __shfl_sync(kFull, vb, lane + 1 + ll_l);
                 const uint32_t o_hi = __shfl_sync(kFull, vb, lane + 2 + ll_l);
@@ -96,10 +91,10 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
                     // Java's normal-path conditions (Lz4RawDecompressor.java:82): literals end 8 bytes before the input end
                     // and 12 bytes before the output end
                     if (lit_end + 8 > (uint32_t) in_len || opw + ll + 12 > (uint32_t) out_cap) break;
-                    const uint32_t off = (uint32_t) __ldg(in + lit_end) | ((uint32_t) __ldg(in + lit_end + 1) << 8);
+                    const uint32_t off = (uint32_t) __ldg(in + lit_end) | ((uint32_t) __ldg(in + (lit_end + 1)) << 8);
                     uint32_t used = pos + ll + 2;
                     if (ml == 15) {
-                        const uint32_t x = __ldg(in + lit_end + 2);
+                        const uint32_t x = __ldg(in + (lit_end + 2));
                         if (x == 255) break;
                         ml += x;
                         used++;
@@ -107,13 +102,15 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
                     ml += kMinMatch;
                     const uint32_t mop = opw + ll;                               // first output byte of the match
                     if (off - 1 >= mop || (off < 32 && off < ml) || mop + ml + 12 > (uint32_t) out_cap) break;
-                    for (uint32_t i = lane; i < ll; i += 32) out_rd_w[opw + i] = __ldg(in + lit_in + i);
+#pragma unroll 1
+                    for (uint32_t i = lane; i < ll; i += 32) out[opw + i] = __ldg(in + (lit_in + i));
                     __syncwarp();
                     // 32 bytes per round; a round only reads bytes written at least 32 positions earlier, or (off >= ml,
                     // single round) bytes in front of the match
+#pragma unroll 1
                     for (uint32_t base = 0; base < ml; base += 32) {
                         const uint32_t i = base + lane;
-                        if (i < ml) out_rd_w[mop + i] = out_rd[mop + i - off];
+                        if (i < ml) out[mop + i] = out[mop + i - off];
                         __syncwarp();
                     }
                     ipw += used;
@@ -121,7 +118,7 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
                     continue;
                 }
                 const uint32_t ll0 = __shfl_sync(kFull, ll_l, 0), off0 = __shfl_sync(kFull, off_l, 0);
-                if (off0 - 1 >= opw + ll0) { ip = ipw; LZ4_FAIL((int64_t) ipw + ll0 + 3, ACC_R_OFFSET_OUTSIDE); }   // offset == 0 || offset > op
+                if (off0 - 1 >= opw + ll0) { LZ4_FAIL((int64_t) ipw + ll0 + 3, ACC_R_OFFSET_OUTSIDE); }   // offset == 0 || offset > op
                 const uint32_t nx1 = 3 + ll0;                                   // <= 17: always inside the window
                 const uint32_t ll1 = __shfl_sync(kFull, ll_l, nx1), off1 = __shfl_sync(kFull, off_l, nx1);
                 const uint32_t e1 = e0 + __shfl_sync(kFull, n_l, nx1);
@@ -145,20 +142,20 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
                 if (!is_lit && (uint32_t) m >= fk) m -= (int32_t) (fk * (((uint32_t) m * kRcp16[fk]) >> 16));   // m mod offset (offset < 32 here)
                 const int32_t srel = (int32_t) (bk + lk) - (int32_t) fk + m;    // source, relative to op
                 uint32_t need = ((uint32_t) lane < e && !is_lit) ? 256u : 0u;
-                if (need && srel < 0) { val = out_rd[opw + (uint32_t) srel]; need = 0; }   // opw + srel >= 0 (offsets checked)
+                if (need && srel < 0) { val = out[opw + (uint32_t) srel]; need = 0; }   // opw + srel >= 0 (offsets checked)
                 while (__any_sync(kFull, need)) {
                     const uint32_t w = __shfl_sync(kFull, val | need, srel);
                     if (need && !(w & 256u)) { val = w; need = 0; }
                 }
-                if ((uint32_t) lane < e) out_lane[opw] = (uint8_t) val;
+                if ((uint32_t) lane < e) out[opw + (uint32_t) lane] = (uint8_t) val;
                 __syncwarp();
                 ipw += nx;
                 opw += e;
             }
-            ip = ipw;
-            op = opw;
+            ip = (PosT) ipw;
+            op = (PosT) opw;
         }
-        if (kFast == 1 && small && ip + 32 <= in_len && op + 44 <= out_cap) {
+        if (kFast == 1 && small && (int64_t) ip + 32 <= in_len && (int64_t) op + 44 <= out_cap) {
             // one coalesced 32-byte load: lane l holds input byte ip + l (token, literals, offset all inside)
             const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
             const uint32_t vb = __ldg(in + ipw + lane);
@@ -201,22 +198,22 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
         }
         if ((int32_t) ll < 0) LZ4_FAIL(ip, ACC_R_NONE);
 
-        const int64_t lit_end = ip + (int64_t) ll;
-        const int64_t lit_out_limit = op + (int64_t) ll;
-        if (lit_out_limit > fast_output_limit - kMinMatch || lit_end > in_len - (2 + 1 + kLastLiterals)) {
+        const int64_t lit_end = (int64_t) ip + (int64_t) ll;
+        const int64_t lit_out_limit = (int64_t) op + (int64_t) ll;
+        if (lit_out_limit > (int64_t) fast_output_limit - kMinMatch || lit_end > (int64_t) in_len - (2 + 1 + kLastLiterals)) {
             if (lit_out_limit > out_cap) LZ4_FAIL(ip, ACC_R_LAST_LITERAL_OUTSIDE);
             if (lit_end != in_len) LZ4_FAIL(ip, ACC_R_ALL_INPUT_CONSUMED);
             warp_copy(out + op, in + ip, ll, lane);
-            op += ll;
+            op += (PosT) ll;
             break;
         }
         warp_copy(out + op, in + ip, ll, lane);
-        op = lit_out_limit;
-        ip = lit_end;
+        op = (PosT) lit_out_limit;
+        ip = (PosT) lit_end;
 
         const uint32_t offset = ld_u16le(in + ip);
         ip += 2;
-        if ((int64_t) offset > op || offset == 0) LZ4_FAIL(ip, ACC_R_OFFSET_OUTSIDE);
+        if ((int64_t) offset > (int64_t) op || offset == 0) LZ4_FAIL(ip, ACC_R_OFFSET_OUTSIDE);
 
         uint32_t ml = token & 15;
         if (ml == 15) {
@@ -231,17 +228,29 @@ __device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in,
         ml += kMinMatch;
         if ((int32_t) ml < 0) LZ4_FAIL(ip, ACC_R_NONE);
 
-        const int64_t match_out_limit = op + (int64_t) ml;
-        if (match_out_limit > fast_output_limit - kMinMatch) {
-            if (match_out_limit > out_cap - kLastLiterals) LZ4_FAIL(ip, ACC_R_LAST5_LITERALS);
+        const int64_t match_out_limit = (int64_t) op + (int64_t) ml;
+        if (match_out_limit > (int64_t) fast_output_limit - kMinMatch) {
+            if (match_out_limit > (int64_t) out_cap - kLastLiterals) LZ4_FAIL(ip, ACC_R_LAST5_LITERALS);
         }
         __syncwarp();
         warp_match_copy(out + op, offset, ml, lane);
         __syncwarp();
-        op = match_out_limit;
+        op = (PosT) match_out_limit;
     }
-    if (lane == 0) { *out_len = op; *status = 0; }
+    if (lane == 0) { out_len_base[idx] = (int64_t) op; status_base[idx] = 0; }
 #undef LZ4_FAIL
+}
+
+// kFast selects the fast path: 1 = one sequence per step, 2 = up to three sequences per step,
+// 3 = 2 + medium steps for sequences with one length-extension byte.
+template <int kFast = 3>
+__device__ __forceinline__ void lz4_decode_block(const uint8_t *__restrict__ in, int64_t in_len, uint8_t *out, int64_t out_cap,
+                                                 int64_t *out_len_base, int32_t *status_base, uint32_t idx, int lane)
+{
+    if (in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL)
+        lz4_decode_impl<kFast, int32_t>(in, (int32_t) in_len, out, (int32_t) out_cap, out_len_base, status_base, idx, lane);
+    else
+        lz4_decode_impl<0, int64_t>(in, in_len, out, out_cap, out_len_base, status_base, idx, lane);
 }
 
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kTpbThreads) lz4_decompress_tpb_kernel(AccBatc
             const int l = __ffs(m) - 1;
             m &= m - 1;
             const int64_t j = base + l;
-            lz4v1::lz4_decode_block(b.src + b.src_off[j], b.src_len[j], b.dst + b.dst_off[j], b.dst_cap[j], b.out_len + j, b.status + j, lane);
+            lz4v1::lz4_decode_block(b.src + b.src_off[j], b.src_len[j], b.dst + b.dst_off[j], b.dst_cap[j], b.out_len, b.status, (uint32_t) j, lane);
             __syncwarp();
         }
     }

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kT, 2) lz4_decompress_v3_kernel(AccBatch b)
             TICK(t_flush);
         }
         else if (warp == 0) {
-            lz4v1::lz4_decode_block(gin, in_len64, gout, out_cap64, b.out_len + idx, b.status + idx, lane);
+            lz4v1::lz4_decode_block(gin, in_len64, gout, out_cap64, b.out_len, b.status, (uint32_t) idx, lane);
         }
         if (tid == 0) {
             atomicAdd(&g_lz4v3_stats[0], 1ull); atomicAdd(&g_lz4v3_stats[1], fallback ? 1ull : 0ull);

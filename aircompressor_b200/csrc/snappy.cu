@@ -37,6 +37,8 @@ __device__ __forceinline__ int32_t snappy_read_length(const uint8_t *in, int64_t
     return 0;
 }
 
+// kMulti: try multi-element steps (up to four elements per warp step) before the pair path.
+template <bool kMulti>
 __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ in0, int64_t in_len0, uint8_t *out, int64_t out_cap,
                                                     int64_t *out_len, int32_t *status, int lane)
 {
@@ -64,6 +66,60 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
         if (small && ip + 32 <= in_len) {
             const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
             const uint32_t vb = __ldg(in + ipw + lane);
+            if (kMulti && opw + 32 <= (uint32_t) out_cap) {
+                // ---- multi-element step: up to four elements (literals of < 32 bytes, 1- and 2-byte-offset copies) that
+                // lie completely in the 32-byte window and produce at most 32 bytes together.  Every lane first decodes
+                // ITS byte as if it were a tag (output bytes, input bytes, offset), the warp follows the chain
+                // tag -> next tag with two shuffles per element, and every lane resolves the source of one output byte:
+                // a literal of the window, older output (one global load), or a byte another lane produces in this step
+                // (taken by shuffle once that lane has it; dependencies point to lower lanes).  An element is only taken
+                // when it is valid under SnappyRawDecompressor.java:89-216 (offset != 0, offset <= op, output fits);
+                // anything else ends the chain and is left to the paths below, which report errors at the same offsets.
+                const uint32_t kind = vb & 3, hi = vb >> 2;
+                const uint32_t b1 = __shfl_sync(kFull, vb, lane + 1), b2 = __shfl_sync(kFull, vb, lane + 2);
+                uint32_t outn = hi + 1, adv = 3, off = b1 | (b2 << 8);                  // 2-byte-offset copy
+                if (kind == 1) { outn = 4 + (hi & 7); adv = 2; off = ((vb >> 5) << 8) | b1; }
+                if (kind == 0) { adv = hi + 2; off = 0; }                               // literal: offset 0 marks it
+                const bool usable = kind != 3 && !(kind == 0 && hi >= 60) && !(kind != 0 && off == 0) && (uint32_t) lane + adv <= 32 && outn <= 32;
+                const uint32_t A = (usable ? outn : 127u) | ((adv & 63) << 8);
+                const uint32_t a0 = __shfl_sync(kFull, A, 0), o0 = __shfl_sync(kFull, off, 0);
+                const uint32_t n0 = a0 & 127, x1 = a0 >> 8;
+                const bool ok0 = n0 <= 32 && o0 <= opw;                                // copies: 1 <= offset <= op (0 = literal)
+                const uint32_t a1 = __shfl_sync(kFull, A, x1), o1 = __shfl_sync(kFull, off, x1);
+                const uint32_t e1 = n0 + (a1 & 127), x2 = x1 + (a1 >> 8);
+                const bool v1 = ok0 && x1 < 32 && e1 <= 32 && o1 <= opw + n0;
+                if (v1) {
+                    const uint32_t a2 = __shfl_sync(kFull, A, x2), o2 = __shfl_sync(kFull, off, x2);
+                    const uint32_t e2 = e1 + (a2 & 127), x3 = x2 + (a2 >> 8);
+                    const bool v2 = x2 < 32 && e2 <= 32 && o2 <= opw + e1;
+                    const uint32_t a3 = __shfl_sync(kFull, A, x3), o3 = __shfl_sync(kFull, off, x3);
+                    const uint32_t e3 = e2 + (a3 & 127), x4 = x3 + (a3 >> 8);
+                    const bool v3 = v2 && x3 < 32 && e3 <= 32 && o3 <= opw + e2;
+                    const uint32_t e = v3 ? e3 : v2 ? e2 : e1;                          // output bytes of this step
+                    const uint32_t nx = v3 ? x4 : v2 ? x3 : x2;                         // input bytes of this step
+                    // which element produces output byte `lane`
+                    const bool k3 = v3 && (uint32_t) lane >= e2, k2 = v2 && (uint32_t) lane >= e1, k1 = (uint32_t) lane >= n0;
+                    const uint32_t sk = k3 ? x3 : k2 ? x2 : k1 ? x1 : 0u;               // tag position in the window
+                    const uint32_t bk = k3 ? e2 : k2 ? e1 : k1 ? n0 : 0u;               // first output byte of the element
+                    const uint32_t fk = k3 ? o3 : k2 ? o2 : k1 ? o1 : o0;               // offset (0: literal)
+                    const uint32_t t = (uint32_t) lane - bk;
+                    uint32_t val = __shfl_sync(kFull, vb, sk + 1 + t);                  // the literal byte, if it is one
+                    uint32_t m = t;
+                    if (fk != 0 && m >= fk) m -= fk * ((m * kRcp16[fk]) >> 16);         // m mod offset (offset < 32 here)
+                    const int32_t srel = (int32_t) (bk + m) - (int32_t) fk;             // source, relative to op
+                    uint32_t need = ((uint32_t) lane < e && fk != 0) ? 256u : 0u;
+                    if (need && srel < 0) { val = out[opw + (uint32_t) srel]; need = 0; }   // opw + srel >= 0 (offsets checked)
+                    while (__any_sync(kFull, need)) {
+                        const uint32_t w = __shfl_sync(kFull, val | need, srel);
+                        if (need && !(w & 256u)) { val = w; need = 0; }
+                    }
+                    if ((uint32_t) lane < e) out[opw + lane] = (uint8_t) val;
+                    __syncwarp();
+                    ip = ipw + nx;
+                    op = opw + e;
+                    continue;
+                }
+            }
             const uint32_t t0 = __shfl_sync(kFull, vb, 0);
             uint32_t L = 0, p = 0;
             bool ok = true;
@@ -143,7 +199,8 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
 #undef SN_FAIL
 }
 
-__global__ void __launch_bounds__(256) snappy_decompress_kernel(AccBatch b)
+template <bool kMulti, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) snappy_decompress_kernel(AccBatch b)
 {
     const int lane = lane_id();
     for (;;) {
@@ -151,7 +208,7 @@ __global__ void __launch_bounds__(256) snappy_decompress_kernel(AccBatch b)
         if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if ((int64_t) idx >= b.n) break;
-        snappy_decode_block(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
+        snappy_decode_block<kMulti>(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
                             b.out_len + idx, b.status + idx, lane);
     }
 }
@@ -305,14 +362,17 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
 
 }  // namespace
 
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    snappy_decompress_kernel<<<(unsigned) ctas, 256, 0, st>>>(b);
+    if (version == 4) snappy_decompress_kernel<false, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // pair steps only (first round-1 kernel)
+    else if (version == 6) snappy_decompress_kernel<true, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else if (version == 7) snappy_decompress_kernel<true, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else snappy_decompress_kernel<true, 1><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st)

@@ -1,7 +1,11 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 timeout 900 python -m pytest tests/test_gpu_lz_parity.py -x -q -m gpu 2>&1 | tail -5
-for d in 0 4 5; do
+for d in 0 8 6 7; do
   timeout 300 python bench.py --codec lz4 --op decompress --steps 5 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 1 --decoder $d 2>/dev/null | tail -1 > /tmp/l.json
-  python -c "import json; d=json.load(open('/tmp/l.json')); print('decoder $d', round(d['value'],1), 'GiB/s', d['ms_per_step'], 'e2e', round(d['e2e']['value'],1))"
+  python -c "import json; d=json.load(open('/tmp/l.json')); print('lz4 decoder $d', round(d['value'],1), 'GiB/s', round(d['ms_per_step'],2))"
+done
+for d in 0 4; do
+  timeout 300 python bench.py --codec snappy --op decompress --steps 5 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 1 --decoder $d 2>/dev/null | tail -1 > /tmp/l.json
+  python -c "import json; d=json.load(open('/tmp/l.json')); print('snappy decoder $d', round(d['value'],1), 'GiB/s', round(d['ms_per_step'],2))"
 done
