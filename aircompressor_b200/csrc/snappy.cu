@@ -52,21 +52,25 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
         if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_SNAPPY_LEN_GT_CAP); }
         return;
     }
+    // base pointers made opaque so the compiler keeps the two 64-bit sums in registers (see lz4_decode_v1.cuh)
     const uint8_t *in = in0 + br;
+    asm volatile("" : "+l"(in));
+    asm volatile("" : "+l"(out));
+    __builtin_assume(__isGlobal(in));
+    __builtin_assume(__isGlobal(out));
     const int64_t in_len = in_len0 - br;
     const int64_t fast_output_limit = out_cap - 8;
     int64_t ip = 0, op = 0;
 
     const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
+    // multi-element steps run while ip <= ip_lim && op <= op_lim (-1: never)
+    const int32_t ip_lim = (kMulti && small && in_len >= 32 && out_cap >= 32) ? (int32_t) in_len - 32 : -1;
+    const int32_t op_lim = (kMulti && small && in_len >= 32 && out_cap >= 32) ? (int32_t) out_cap - 32 : -1;
     while (ip < in_len) {
-        // ---- fast path: [literal of <= 27 bytes] + [one 1- or 2-byte-offset copy], parsed from one coalesced 32-byte load.
-        // Every output byte is resolved independently (a literal byte of this step, or older output through the periodic
-        // source formula), so the step is one load and one store per lane and 32-byte chunk.  The bounds make the elements
-        // valid under SnappyRawDecompressor.java:89-216; anything else goes to the element-by-element path below.
-        if (small && ip + 32 <= in_len) {
-            const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
-            const uint32_t vb = __ldg(in + ipw + lane);
-            if (kMulti && opw + 32 <= (uint32_t) out_cap) {
+        if (kMulti) {
+            uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
+            while ((int32_t) ipw <= ip_lim && (int32_t) opw <= op_lim) {
+                const uint32_t vb = __ldg(in + (ipw + (uint32_t) lane));
                 // ---- multi-element step: up to four elements (literals of < 32 bytes, 1- and 2-byte-offset copies) that
                 // lie completely in the 32-byte window and produce at most 32 bytes together.  Every lane first decodes
                 // ITS byte as if it were a tag (output bytes, input bytes, offset), the warp follows the chain
@@ -88,7 +92,8 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
                 const uint32_t a1 = __shfl_sync(kFull, A, x1), o1 = __shfl_sync(kFull, off, x1);
                 const uint32_t e1 = n0 + (a1 & 127), x2 = x1 + (a1 >> 8);
                 const bool v1 = ok0 && x1 < 32 && e1 <= 32 && o1 <= opw + n0;
-                if (v1) {
+                if (!v1) break;
+                {
                     const uint32_t a2 = __shfl_sync(kFull, A, x2), o2 = __shfl_sync(kFull, off, x2);
                     const uint32_t e2 = e1 + (a2 & 127), x3 = x2 + (a2 >> 8);
                     const bool v2 = x2 < 32 && e2 <= 32 && o2 <= opw + e1;
@@ -115,11 +120,21 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
                     }
                     if ((uint32_t) lane < e) out[opw + lane] = (uint8_t) val;
                     __syncwarp();
-                    ip = ipw + nx;
-                    op = opw + e;
-                    continue;
+                    ipw += nx;
+                    opw += e;
                 }
             }
+            ip = ipw;
+            op = opw;
+            if (ip >= in_len) break;
+        }
+        // ---- fast path: [literal of <= 27 bytes] + [one 1- or 2-byte-offset copy], parsed from one coalesced 32-byte load.
+        // Every output byte is resolved independently (a literal byte of this step, or older output through the periodic
+        // source formula), so the step is one load and one store per lane and 32-byte chunk.  The bounds make the elements
+        // valid under SnappyRawDecompressor.java:89-216; anything else goes to the element-by-element path below.
+        if (small && ip + 32 <= in_len) {
+            const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
+            const uint32_t vb = __ldg(in + ipw + lane);
             const uint32_t t0 = __shfl_sync(kFull, vb, 0);
             uint32_t L = 0, p = 0;
             bool ok = true;
@@ -372,7 +387,7 @@ void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_
     if (version == 4) snappy_decompress_kernel<false, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // pair steps only (first round-1 kernel)
     else if (version == 6) snappy_decompress_kernel<true, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
     else if (version == 7) snappy_decompress_kernel<true, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else snappy_decompress_kernel<true, 1><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else snappy_decompress_kernel<true, 5><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st)
