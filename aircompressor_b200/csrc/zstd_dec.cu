@@ -19,9 +19,16 @@ using namespace zs;
 constexpr int kWarpsPerCta = 4;
 constexpr int kSeqBatch = 32;
 
+// The Huffman table (needed while the literals of a block are decoded) and the three FSE tables (needed while its
+// sequences are decoded) share one 8 KiB region: 10.2 KiB of shared memory per warp instead of 15.2, i.e. 20 resident
+// warps per SM instead of 12 (the kernel is latency bound: lane 0 walks the FSE states alone).  Tables that a later
+// block or frame of the same input may reuse (treeless literals, repeat-mode sequence tables) are parked in the
+// warp's global scratch (kHufSave / kFseSave) whenever more input follows the current block.
 struct WarpSmem {
-    uint16_t huf[4096];       // symbol | nbits << 8
-    uint32_t ll[512], ml[512], of[256];
+    union {
+        uint16_t huf[4096];   // symbol | nbits << 8
+        struct { uint32_t ll[512], ml[512], of[256]; };
+    };
     uint32_t wt[64];          // FSE table of the Huffman weights (must not clobber ll/ml/of: repeat mode reuses them)
     int16_t norm[256];
     int16_t next[256];
@@ -286,8 +293,21 @@ __device__ __forceinline__ void copy_literals(uint8_t *dst, const Literals &lit,
 
 // decodes one compressed block (ZstdFrameDecompressor.decodeCompressedBlock :265-310 + decompressSequences :312-516).
 // Returns bytes produced or -1.  `out`/`out_pos` are relative to the start of the caller's output buffer.
+// copies n_bytes (a multiple of 16) between 16-byte aligned buffers with the whole warp
+__device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n_bytes, int lane)
+{
+    uint4 *d = (uint4 *) dst;
+    const uint4 *q = (const uint4 *) src;
+    for (int i = lane; i < n_bytes / 16; i += 32) d[i] = q[i];
+    __syncwarp();
+}
+
+constexpr int kHufBytes = 4096 * 2, kFseBytes = (512 + 512 + 256) * 4;
+constexpr int64_t kHufSave = kMaxBlock + 256, kFseSave = kHufSave + kHufBytes;   // offsets in the warp's scratch
+
 __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int block_size, uint8_t *out,
-                                           int64_t out_pos, int64_t out_cap, int32_t window_size, uint8_t *lit_scratch, Ctl &ctl, int lane)
+                                           int64_t out_pos, int64_t out_cap, int32_t window_size, uint8_t *lit_scratch, bool keep_tables,
+                                           Ctl &ctl, int lane)
 {
     int64_t input = in_addr;
     const int64_t block_end = in_addr + block_size;
@@ -347,6 +367,12 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
             int64_t used = huf_read_table(sm, fs, in, input, comp_size, ctl, lane);
             if (used < 0) return -1;
             input += used;
+            if (keep_tables) warp_copy16(lit_scratch + kHufSave, sm.huf, kHufBytes, lane);
+        }
+        else {
+            // treeless literals: the table of an earlier block (parked when it was built: something followed that block)
+            __syncwarp();
+            warp_copy16(sm.huf, lit_scratch + kHufSave, kHufBytes, lane);
         }
         // streams
         int reason = 0;
@@ -408,6 +434,12 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
         // computeLiteralsTable / computeOffsetsTable / computeMatchLengthTable :609-676 (lane 0 builds, result broadcast)
         int64_t tb_ret = 0;
         int lg[3] = {fs.ll_log, fs.of_log, fs.ml_log};
+        __syncwarp();   // the literal streams are done with the Huffman table: the region now holds the FSE tables
+        if ((type >> 6) == 3 || ((type >> 4) & 3) == 3 || ((type >> 2) & 3) == 3) {
+            // repeat mode: bring back the tables of the previous sequence section of this frame (if there is none the
+            // lg[k] >= 0 check below rejects the block before anything is used)
+            warp_copy16(sm.ll, lit_scratch + kFseSave, kFseBytes, lane);
+        }
         if (lane == 0) {
             tb_ret = [&]() -> int64_t {
                 const int types[3] = {(int) (type >> 6), (int) ((type >> 4) & 3), (int) ((type >> 2) & 3)};
@@ -450,6 +482,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
         fs.of_log = __shfl_sync(kFull, lg[1], 0);
         fs.ml_log = __shfl_sync(kFull, lg[2], 0);
         __syncwarp();
+        if (keep_tables) warp_copy16(lit_scratch + kFseSave, sm.ll, kFseBytes, lane);
 
         // lane 0 owns the bit reader and the three FSE states; sequences are produced in batches of 32 and
         // executed by the whole warp.
@@ -620,7 +653,10 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
             }
             else if (block_type == 2) {
                 ZCHECK(input + block_size <= in_len, input, R_NOT_ENOUGH_INPUT);
-                decoded = decode_compressed_block(sm, fs, in, input, block_size, out, output, out_cap, window_size, lit_scratch, ctl, lane);
+                // does anything follow this block in the input (another block, or another frame after the checksum)?
+                const bool more_follows = !last_block || input + block_size + (has_checksum ? 4 : 0) < in_len;
+                decoded = decode_compressed_block(sm, fs, in, input, block_size, out, output, out_cap, window_size, lit_scratch, more_follows,
+                                                  ctl, lane);
                 if (decoded < 0) return -1;
                 input += block_size;
             }
@@ -644,7 +680,7 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
     return output;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
 {
     extern __shared__ __align__(16) uint8_t zsmem[];
     const int lane = lane_id();
@@ -669,9 +705,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) zstd_decompress_kernel(AccB
 
 }  // namespace
 
-static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256;
+static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256 + kHufBytes + kFseBytes;   // literals | parked Huffman table | parked FSE tables
 
-int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * 3; }   // 3 CTAs x 4 warps per SM (shared memory bound)
+int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * 5; }   // 5 CTAs x 4 warps per SM (shared memory bound)
 
 int64_t acc_zstd_dec_scratch_bytes(int sm_count) { return acc_zstd_dec_grid(sm_count) * kWarpsPerCta * kZstdDecScratchPerWarp; }
 
