@@ -215,12 +215,12 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
 // ---- pipelined host-pointer path ---------------------------------------------------------------------
 // A large batch is cut into runs of consecutive blocks; run k's input upload (copy stream 1), its kernel (the
 // caller's stream) and its output download (copy stream 2) overlap with the neighbours' so that the call costs about
-// max(H2D, kernels, D2H) instead of their sum. Runs hold >= 8192 blocks: the decoders give one warp per block, and a
-// launch with fewer blocks than resident warps is bound by single-block latency, not throughput.
+// max(H2D, kernels, D2H) instead of their sum. Runs hold >= 4096 blocks: the decoders give one warp per block, and a
+// launch with far fewer blocks than resident warps is bound by single-block latency, not throughput.
 static int pipeline_chunks(acc_ctx *c, int64_t n, int64_t bytes, const int64_t *src_off)
 {
     if (c->tuning_pipeline == 1) return 1;
-    int64_t k = c->tuning_pipeline > 1 ? c->tuning_pipeline : std::min<int64_t>(n / 8192, bytes / (32 << 20));
+    int64_t k = c->tuning_pipeline > 1 ? c->tuning_pipeline : std::min<int64_t>(n / 4096, bytes / (32 << 20));
     if (k > acc_ctx::kMaxChunks) k = acc_ctx::kMaxChunks;
     if (k > n) k = n;
     if (k < 2) return 1;

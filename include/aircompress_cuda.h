@@ -149,7 +149,7 @@ int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t 
  * key 0: resident CTAs per SM for the warp-per-block decode kernels; key 1: LZ4 decoder (1 = warp per block,
  * 2 = thread per block, 3 = shared-memory window); key 2: CTA count of the thread-per-block decoder;
  * key 3: host-pointer batches, 1 = never split, k > 1 = split into k overlapped upload/kernel/download runs
- * (default: automatic for batches of >= 16384 blocks and >= 64 MiB); other keys are ignored. */
+ * (default: automatic, up to 16 runs of >= 4096 blocks and >= 32 MiB each); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);
 
 #ifdef __cplusplus

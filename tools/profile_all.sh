@@ -6,7 +6,9 @@ prof() { # name codec op kernel-regex blocks
   tail -1 gpurun_out/ncu_$1.log | cut -c1-120
 }
 prof lz4_decompress lz4 decompress lz4_decompress_kernel 65536
-prof lz4_compress lz4 compress lz4_compress_kernel 16384
+# launches alternate 16-bit-table / 32-bit-table instantiation (the second exits at once for 64 KiB blocks): skip 4 -> a 16-bit one
+prof4() { ncu --set full --clock-control none --import-source on -k regex:$4 -s 4 -c 1 -o gpurun_out/prof_r1_$1 python bench.py --profile --codec $2 --op $3 --steps 1 --warmup 3 --blocks $5 > gpurun_out/ncu_$1.log 2>&1; tail -1 gpurun_out/ncu_$1.log | cut -c1-120; }
+prof4 lz4_compress lz4 compress lz4_compress_kernel 16384
 prof snappy_decompress snappy decompress snappy_decompress_kernel 32768
 prof snappy_compress snappy compress snappy_compress_kernel 16384
 prof zstd_decompress zstd decompress zstd_decompress_kernel 8192
