@@ -1,9 +1,9 @@
 """Lane-level emulation (numpy, 32 lanes) of the multi-sequence LZ4 fast path in lz4_decode_v1.cuh, checked against the
 oracle on corpus blocks and corrupted streams.  Development aid: validates the index arithmetic of the kernel on the CPU
-before GPU time is spent.  python tools/lz4_multiseq_emu.py"""
+before GPU time is spent.  python tests/emu/lz4_multiseq_emu.py (also run by tests/test_step_emulators.py)"""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 
 LANE = np.arange(32, dtype=np.int64)
 STAT = {"iters": 0, "seqs": 0, "rounds": 0, "slow": 0}
@@ -176,14 +176,15 @@ def decode(inp, out_cap, KMAX=3):
 REASON = {1: "INPUT_EMPTY", 2: "LAST_LITERAL_OUTSIDE", 3: "ALL_INPUT_CONSUMED", 4: "OFFSET_OUTSIDE", 5: "LAST5_LITERALS", 6: "ZERO_CAP", 0: "NONE"}
 
 
-def main():
+def main(o=None, n_cases=40):
     import benchdata
-    from oracle.pyoracle import Oracle, OracleError
-    o = Oracle()
+    if o is None:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
     full = os.path.join(benchdata.ROOT, "corpus", "silesia")
     blob = np.fromfile(os.path.join(benchdata.ROOT, "tests", "golden", "silesia_sample.bin"), dtype=np.uint8)
     rng = np.random.default_rng(5)
-    starts = rng.integers(0, len(blob) - 16384, size=40)
+    starts = rng.integers(0, len(blob) - 16384, size=n_cases)
     cases = []
     for st in starts:
         sz = int(rng.choice([300, 2000, 8192, 16384]))
@@ -214,6 +215,7 @@ def main():
                 bad += 1
                 print("MISMATCH", (st, ln), eo, len(comp), cap)
     print("checked", checked, "bad", bad, STAT, "seq/iter", STAT["seqs"] / max(1, STAT["iters"]), "rounds/iter", STAT["rounds"] / max(1, STAT["iters"]))
+    return checked, bad, dict(STAT)
 
 
 if __name__ == "__main__":

@@ -1,8 +1,8 @@
 """Lane-level emulation (numpy, 32 lanes) of the multi-element Snappy decode step in snappy.cu, checked against the
-oracle on corpus blocks and corrupted streams.  Development aid (see lz4_multiseq_emu.py).  python tools/snappy_multi_emu.py"""
+oracle on corpus blocks and corrupted streams.  Development aid (see lz4_multiseq_emu.py).  python tests/emu/snappy_multi_emu.py (also run by tests/test_step_emulators.py)"""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 
 LANE = np.arange(32, dtype=np.int64)
 STAT = {"multi": 0, "elems": 0, "pair": 0, "slow": 0, "rounds": 0}
@@ -174,13 +174,14 @@ def decode(inp, out_cap):
 REASON = {0: "NONE", 7: "TRUNCATED", 8: "VARINT_HIGHBIT", 9: "NEG_LENGTH", 10: "LEN_GT_CAP", 11: "LEN_MISMATCH"}
 
 
-def main():
+def main(o=None, n_cases=40):
     import benchdata
-    from oracle.pyoracle import Oracle
-    o = Oracle()
+    if o is None:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
     blob = np.fromfile(os.path.join(benchdata.ROOT, "tests", "golden", "silesia_sample.bin"), dtype=np.uint8)
     rng = np.random.default_rng(7)
-    starts = rng.integers(0, len(blob) - 16384, size=40)
+    starts = rng.integers(0, len(blob) - 16384, size=n_cases)
     cases = []
     for st in starts:
         sz = int(rng.choice([300, 2000, 8192, 16384]))
@@ -208,6 +209,7 @@ def main():
                 bad += 1
                 print("MISMATCH", (st, ln), eo, len(comp), cap)
     print("checked", checked, "bad", bad, STAT, "elems/multi", STAT["elems"] / max(1, STAT["multi"]))
+    return checked, bad, dict(STAT)
 
 
 if __name__ == "__main__":
