@@ -330,7 +330,7 @@ def main():
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) ----------------
     e2e = None
     try:
-        if args.profile or args.op == "hash":
+        if args.profile or args.op == "hash" or args.e2e_steps <= 0:
             raise RuntimeError("skipped")
         h_src = torch.empty(src_d.numel(), dtype=torch.uint8, pin_memory=True)
         h_src.copy_(src_d)
