@@ -199,13 +199,13 @@ void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm,
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    // default: multi-sequence + medium steps, registers bounded for 6 resident CTAs (40 registers, 48 warps per SM):
-    // 234 GiB/s vs 228 (5 CTAs), 200 (unbounded, 63 registers, 4 CTAs) and 234 (8 CTAs, more spills) on the bench batch
+    // default: multi-sequence + medium steps, registers bounded for 8 resident CTAs (32 registers, 64 warps per SM):
+    // 253 GiB/s vs 248 (6 CTAs, 40 registers) and ~200 (unbounded: 63 registers, 4 CTAs) on the bench batch
     if (version == 4) lz4_decompress_kernel<1, 1><<<(unsigned) ctas, 256, 0, st>>>(b);        // one sequence per step (first round-1 kernel)
     else if (version == 5) lz4_decompress_kernel<2, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // multi-sequence steps only
-    else if (version == 7) lz4_decompress_kernel<3, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else if (version == 6) lz4_decompress_kernel<3, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
     else if (version == 8) lz4_decompress_kernel<3, 1><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else lz4_decompress_kernel<3, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
+    else lz4_decompress_kernel<3, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter)

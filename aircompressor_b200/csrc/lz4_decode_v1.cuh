@@ -46,9 +46,6 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
     // literals / itself -- the literal it ultimately repeats) and the whole sequence is a single
     // load + store per lane.  The bounds below are exactly the conditions under which the Java decoder
     // takes its normal (non-final) path (Lz4RawDecompressor.java:82,168), so results are identical.
-    // multi-sequence steps run while ip <= ip_lim && op <= op_lim (-1: never)
-    const int32_t ip_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) in_len - 40 : -1;
-    const int32_t op_lim = (small && in_len >= 40 && out_cap >= 44) ? (int32_t) out_cap - 44 : -1;
     while (ip < in_len) {
         if (small && kFast >= 2) {
             // ---- multi-sequence steps: up to three short sequences (no length-extension bytes) whose tokens, literals
@@ -63,24 +60,18 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
             // decoder's conditions for the normal (non-final) path (Lz4RawDecompressor.java:82,168); a sequence with a bad
             // offset is left for the next step to report (it then is sequence 0), so error offsets are unchanged.
             uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
-            while ((int32_t) ipw <= ip_lim && (int32_t) opw <= op_lim) {
+            while ((int32_t) (ipw + 40) <= in_len && (int32_t) (opw + 44) <= out_cap) {   // positions < 2^31 - 256: no wrap
                 const uint32_t vb = __ldg(in + (ipw + (uint32_t) lane));
-                const uint32_t ll_l = vb >> 4, ml_l = vb & 15;
-                const uint32_t o_lo = __shfl_sync(kFull, vb, lane + 1 + ll_l);
-                const uint32_t o_hi = __shfl_sync(kFull, vb, lane + 2 + ll_l);
-                const uint32_t off_l = o_hi * 256 + o_lo;
-                // output bytes of a sequence starting at this lane; 63 (never fits) when it needs the general path
-                const uint32_t n_l = (vb < 0xF0 && ml_l != 15 && (uint32_t) lane + ll_l <= 29) ? ll_l + ml_l + kMinMatch : 63u;
-                const uint32_t e0 = __shfl_sync(kFull, n_l, 0);
-                if (e0 > 32) {
+                const uint32_t tok = __shfl_sync(kFull, vb, 0);
+                const uint32_t ll0 = tok >> 4, ml0 = tok & 15;
+                if (ll0 == 15 || ml0 == 15) {
                     if (kFast != 3) break;
                     // ---- medium step: ONE sequence whose literal and/or match length carries a single extension byte
-                    // (lengths up to 269 / 273; 92 % of the sequences the steps above cannot take).  Anything unusual --
+                    // (lengths up to 269 / 273; 92 % of the sequences the steps below cannot take).  Anything unusual --
                     // a second extension byte, the end-of-block rules, a bad offset, a match overlapping itself at a
                     // distance below 32 -- leaves through `break` BEFORE ip/op move, and the general path below decodes
                     // the sequence again from its token (and reports the error, if there is one).
-                    const uint32_t tok = __shfl_sync(kFull, vb, 0);
-                    uint32_t ll = tok >> 4, ml = tok & 15, pos = 1;
+                    uint32_t ll = ll0, ml = ml0, pos = 1;
                     if (ll == 15) {
                         const uint32_t x = __shfl_sync(kFull, vb, 1);
                         if (x == 255) break;
@@ -91,10 +82,17 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
                     // Java's normal-path conditions (Lz4RawDecompressor.java:82): literals end 8 bytes before the input end
                     // and 12 bytes before the output end
                     if (lit_end + 8 > (uint32_t) in_len || opw + ll + 12 > (uint32_t) out_cap) break;
-                    const uint32_t off = (uint32_t) __ldg(in + lit_end) | ((uint32_t) __ldg(in + (lit_end + 1)) << 8);
-                    uint32_t used = pos + ll + 2;
+                    const uint32_t wend = pos + ll;                              // window position of the offset bytes
+                    uint32_t off, used = wend + 2, x = 0;
+                    if (wend + 2 < 32) {                                         // offset and extension byte are in the window
+                        off = __shfl_sync(kFull, vb, wend) | (__shfl_sync(kFull, vb, wend + 1) << 8);
+                        x = __shfl_sync(kFull, vb, wend + 2);
+                    }
+                    else {
+                        off = (uint32_t) __ldg(in + lit_end) | ((uint32_t) __ldg(in + (lit_end + 1)) << 8);
+                        if (ml == 15) x = __ldg(in + (lit_end + 2));
+                    }
                     if (ml == 15) {
-                        const uint32_t x = __ldg(in + (lit_end + 2));
                         if (x == 255) break;
                         ml += x;
                         used++;
@@ -102,8 +100,14 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
                     ml += kMinMatch;
                     const uint32_t mop = opw + ll;                               // first output byte of the match
                     if (off - 1 >= mop || (off < 32 && off < ml) || mop + ml + 12 > (uint32_t) out_cap) break;
+                    if (wend <= 32) {                                            // all literals are in the window
+                        const uint32_t v = __shfl_sync(kFull, vb, lane + pos);
+                        if ((uint32_t) lane < ll) out[opw + (uint32_t) lane] = (uint8_t) v;
+                    }
+                    else {
 #pragma unroll 1
-                    for (uint32_t i = lane; i < ll; i += 32) out[opw + i] = __ldg(in + (lit_in + i));
+                        for (uint32_t i = lane; i < ll; i += 32) out[opw + i] = __ldg(in + (lit_in + i));
+                    }
                     __syncwarp();
                     // 32 bytes per round; a round only reads bytes written at least 32 positions earlier, or (off >= ml,
                     // single round) bytes in front of the match
@@ -117,7 +121,16 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
                     opw = mop + ml;
                     continue;
                 }
-                const uint32_t ll0 = __shfl_sync(kFull, ll_l, 0), off0 = __shfl_sync(kFull, off_l, 0);
+                // per-lane candidates: what a sequence starting at this lane's byte would be
+                const uint32_t ll_l = vb >> 4, ml_l = vb & 15;
+                const uint32_t o_lo = __shfl_sync(kFull, vb, lane + 1 + ll_l);
+                const uint32_t o_hi = __shfl_sync(kFull, vb, lane + 2 + ll_l);
+                const uint32_t off_l = o_hi * 256 + o_lo;
+                // output bytes of a sequence starting at this lane; >= 64 (never fits) when it needs the other paths
+                uint32_t n_l = ll_l + ml_l + kMinMatch;
+                if (vb >= 0xF0 || ml_l == 15 || (uint32_t) lane + ll_l > 29) n_l |= 64u;
+                const uint32_t e0 = ll0 + ml0 + kMinMatch;                      // <= 32
+                const uint32_t off0 = __shfl_sync(kFull, off_l, 0);
                 if (off0 - 1 >= opw + ll0) { LZ4_FAIL((int64_t) ipw + ll0 + 3, ACC_R_OFFSET_OUTSIDE); }   // offset == 0 || offset > op
                 const uint32_t nx1 = 3 + ll0;                                   // <= 17: always inside the window
                 const uint32_t ll1 = __shfl_sync(kFull, ll_l, nx1), off1 = __shfl_sync(kFull, off_l, nx1);
