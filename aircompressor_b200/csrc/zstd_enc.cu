@@ -35,6 +35,14 @@ constexpr int kStreamStage = 48 * 1024;                  // staging bytes per Hu
 constexpr int kSeqStage = kMaxBlock + 1024;              // staging bytes for the sequence bitstream
 constexpr int64_t kScratchPerCta = (int64_t) kMaxSeq * 8 + (kMaxBlock + 64) + (int64_t) 3 * kMaxSeq * 2 + 4 * kStreamStage + kSeqStage + 256;
 
+// Slot of a 4-byte value in the position table.  Every warp owns one eighth of the table (its sub-range of the block only
+// ever sees its own insertions), which makes the encoder deterministic: with one shared table the candidate a warp read
+// depended on how far the other warps had come.
+__device__ __forceinline__ uint32_t zenc_slot(uint32_t v, int warp)
+{
+    return ((v * 2654435761u) >> (32 - (kHashLog - 3))) | ((uint32_t) warp << (kHashLog - 3));
+}
+
 struct NodeTable { int32_t count[512]; int16_t parents[512]; int16_t symbols[512]; uint8_t nbits[512]; };
 
 struct EncSmem {
@@ -351,14 +359,14 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         uint32_t cand = 0xFFFFFFFFu, cur = 0;
                         if (p < probe_limit) {
                             cur = ld_u32_unaligned(blk + p);
-                            uint32_t h = (cur * 2654435761u) >> (32 - kHashLog);
+                            const uint32_t h = zenc_slot(cur, warp);
                             cand = sm.u.hash[h];
                             if (cand < (uint32_t) p && ld_u32_unaligned(blk + cand) == cur) hit = true;
                         }
                         __syncwarp();
                         const unsigned hits = __ballot_sync(kFull, hit);
                         const int first_hit = hits ? __ffs(hits) - 1 : 31;
-                        if (p < probe_limit && lane <= first_hit) sm.u.hash[(cur * 2654435761u) >> (32 - kHashLog)] = (uint32_t) p;   // see lz4.cu
+                        if (p < probe_limit && lane <= first_hit) sm.u.hash[zenc_slot(cur, warp)] = (uint32_t) p;   // see lz4.cu
                         if (hits == 0) { pos += 32; continue; }
                         const int first = __ffs(hits) - 1;
                         int mpos = pos + first;
