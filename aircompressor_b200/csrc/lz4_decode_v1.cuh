@@ -1,6 +1,10 @@
-// lz4_decode_v1.cuh -- exact warp-per-block LZ4 decoder (bit-exact with Lz4RawDecompressor.java:35-198, including
-// every reject decision and error offset).  Used directly by lz4_decompress_kernel and as the fallback of the
-// shared-memory-window decoder in lz4_v3.cu.
+// lz4_decode_v1.cuh -- warp-per-block LZ4 block decoder, bit-exact with Lz4RawDecompressor.java:35-198 including every
+// reject decision and error offset.  Three layers, fastest first; each layer only takes what it can prove valid and leaves
+// everything else (and all error reporting) to the next one:
+//   1. multi-sequence steps: up to three sequences without length-extension bytes per 32-byte window (kFast >= 2)
+//   2. medium steps: one sequence with a single extension byte per length (kFast == 3)
+//   3. the general path: a restatement of the Java loop, sequence by sequence, with warp-wide copies
+// Used by lz4_decompress_kernel (lz4.cu) and as the fallback of the experimental decoders in lz4_v3.cu / lz4_tpb.cu.
 #pragma once
 #include "acc_device.cuh"
 
@@ -10,8 +14,7 @@ constexpr int kMinMatch = 4;
 constexpr int kLastLiterals = 5;
 
 // ------------------------------------------------------------------------------------------------
-// Decode: one warp per block.  All lanes walk the token stream redundantly (broadcast loads), the
-// literal and match copies are spread over the 32 lanes.
+// Decode: one warp per block; `lane` is the caller's lane id, results go to out_len_base[idx] / status_base[idx].
 // ------------------------------------------------------------------------------------------------
 // PosT is the type of the positions: int32_t for blocks below 2 GiB (the normal case: half the registers and
 // instructions), int64_t otherwise (no fast paths).  Sums that can leave the int32 range are formed in int64.

@@ -39,6 +39,25 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def best_thread_count(run_pass, max_threads):
+    """The CPU arm should show the reference at its best on this box: with SMT siblings or a CPU quota, fewer threads than
+    the affinity mask offers can be faster.  Times one pass (after one warm-up) at N, N/2, N/4, N/8 threads and returns the
+    fastest count."""
+    best, best_dt = max_threads, None
+    t = max_threads
+    tried = set()
+    while t >= 1 and len(tried) < 4:
+        tried.add(t)
+        run_pass(t)
+        t0 = time.perf_counter()
+        run_pass(t)
+        dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best, best_dt = t, dt
+        t //= 2
+    return best
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -155,6 +174,7 @@ def run_reference(args, rank, world):
         doff = np.arange(n_sample, dtype=np.int64) * bound
         unc = int(slen.sum())
         dst = np.zeros(int(bound * n_sample), dtype=np.uint8)
+    threads = best_thread_count(lambda t: orc.batch(op, src, soff, slen, dst, doff, dcap, threads=t), threads)
     for _ in range(args.warmup):
         orc.batch(op, src, soff, slen, dst, doff, dcap, threads=threads)
     t0 = time.perf_counter()
@@ -169,7 +189,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": f"synthetic batch: {wl['label']}",
         "config": {"workload": f"{args.codec} block {args.op}, {args.block_kib} KiB blocks x {args.blocks} batch per GPU",
-                   "note": "reference CPU algorithm (C restatement of the Java codec, oracle/), one call per block, OpenMP over blocks"},
+                   "note": "reference CPU algorithm (C restatement of the Java codec, oracle/), one call per block, OpenMP over blocks; thread count = fastest of N, N/2, N/4, N/8"},
         "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -411,14 +431,14 @@ def main():
             doff, dcap = np.arange(ns, dtype=np.int64) * b, np.full(ns, b, dtype=np.int64)
             unc_s = int(slen.sum())
         dst = np.zeros(int(doff[-1] + dcap[-1]), dtype=np.uint8)
-        orc.batch(op, src, soff, slen, dst, doff, dcap, threads=threads)
+        cpu_threads = best_thread_count(lambda t: orc.batch(op, src, soff, slen, dst, doff, dcap, threads=t), threads)
         reps, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 8.0:
-            orc.batch(op, src, soff, slen, dst, doff, dcap, threads=threads)
+            orc.batch(op, src, soff, slen, dst, doff, dcap, threads=cpu_threads)
             reps += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": unc_s * reps / dt / GiB, "unit": "GiB/s", "cores": threads, "kind": "port",
-                        "sample": f"{ns} blocks x {args.block_kib} KiB x {reps} passes, all {threads} host threads, one call per block"}
+        cpu_baseline = {"value": unc_s * reps / dt / GiB, "unit": "GiB/s", "cores": cpu_threads, "kind": "port",
+                        "sample": f"{ns} blocks x {args.block_kib} KiB x {reps} passes, {cpu_threads} of {threads} host threads (fastest of N, N/2, N/4, N/8), one call per block"}
 
     line = {
         "metric": f"{args.codec}_{args.op}_uncompressed_GiB_per_s", "value": value, "unit": "GiB/s", "n_gpus": world,

@@ -115,3 +115,21 @@ def test_small_literal_roundtrip(oracle, refnative, codec):
 def test_max_compressed_length(oracle):
     assert oracle.max_compressed_length("lz4", 65536) == 65809
     assert oracle.max_compressed_length("snappy", 65536) == 76490
+
+
+def test_config0_lz4_whole_file_roundtrip_single_thread(oracle, refnative, pieces):
+    """BASELINE.json configs[0] (CPU plumbing, no GPU): the reference calls the codec on whole files
+    (AbstractTestCompression.java:362-393).  The LZ4 port compresses and decompresses the whole corpus sample as ONE input,
+    single-threaded, the result is byte-identical, and the reference's bundled liblz4 decodes the same stream."""
+    import time
+    whole = np.concatenate(pieces).tobytes()
+    t0 = time.perf_counter()
+    c = oracle.compress("lz4", whole)
+    t1 = time.perf_counter()
+    back = oracle.decompress("lz4", c, len(whole))
+    t2 = time.perf_counter()
+    assert back == whole
+    assert refnative.decompress("lz4", c, len(whole)) == whole
+    assert len(c) <= oracle.max_compressed_length("lz4", len(whole))
+    mib = len(whole) / (1 << 20)
+    print(f"lz4 port, 1 thread, {mib:.1f} MiB: compress {mib / (t1 - t0):.0f} MiB/s, decompress {mib / (t2 - t1):.0f} MiB/s, ratio {len(c) / len(whole):.3f}")
