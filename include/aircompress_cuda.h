@@ -123,7 +123,9 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
  * block i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes at most dst_cap[i] bytes at
  * dst_base + dst_off[i].  `stream` is a CUstream/cudaStream_t handle (0 = the context's own non-blocking
  * stream; pass 1 (cudaStreamLegacy) or 2 (cudaStreamPerThread) to target CUDA's default streams);
- * with ACC_F_DEVICE_POINTERS the work is only enqueued.  Without it the library copies host->device,
+ * with ACC_F_DEVICE_POINTERS the work is only enqueued (at most 100 batches may be in flight per context:
+ * every launch takes one or two of the context's 256 work-stealing counters, which are reused round-robin).
+ * Without it the library copies host->device,
  * runs, copies results back and synchronises before returning; large batches are cut into runs of consecutive
  * blocks whose upload, kernel and download overlap (see acc_set_tuning key 3).
  * Output contract: bytes [0, out_len[i]) of window i are the result; the rest of the window
