@@ -219,6 +219,10 @@ class XxHash64CudaHasher:
         h = self._L.acc_xxh64(self._ctx.handle, src.ctypes.data + offset, length, C.c_int64(_to_signed(seed)).value)
         return h & 0xFFFFFFFFFFFFFFFF
 
+    def hashLong(self, value, seed=0):
+        """hash(long value[, long seed]) (XxHash64Hasher.java:44-53): the 8 bytes of `value` in little-endian order."""
+        return self.hash((value & 0xFFFFFFFFFFFFFFFF).to_bytes(8, "little"), 0, 8, seed)
+
     def close(self):
         self._ctx.close()
 

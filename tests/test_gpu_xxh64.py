@@ -30,3 +30,16 @@ def test_xxh64_seeded_single_call(oracle):
     data = bytes(range(256)) * 33
     for seed in (0, 1, PRIME32, 0xFFFFFFFFFFFFFFFF):
         assert h.hash(data, 3, 4000, seed) == oracle.xxh64(data[3:4003], seed)
+
+
+def test_xxh64_hash_long(oracle):
+    # AbstractTestXxHash64.java:321-364: hash(long) == hash of the 8 little-endian bytes, with and without seed
+    h = acb.XxHash64CudaHasher()
+    PRIME32 = 0x9E3779B1
+    value = 0x0102030405060708
+    assert h.hashLong(value) == h.hash(bytes([8, 7, 6, 5, 4, 3, 2, 1]))
+    assert h.hashLong(value, PRIME32) == h.hash(bytes([8, 7, 6, 5, 4, 3, 2, 1]), seed=PRIME32)
+    for v in (0, 12345, 0x7FFFFFFFFFFFFFFF, 0xDEADBEEFCAFEBABE):
+        for seed in (0, PRIME32):
+            assert h.hashLong(v, seed) == oracle.xxh64_long(v, seed)
+    assert h.hashLong(0) != h.hashLong(0, PRIME32)

@@ -133,3 +133,11 @@ def test_config0_lz4_whole_file_roundtrip_single_thread(oracle, refnative, piece
     assert len(c) <= oracle.max_compressed_length("lz4", len(whole))
     mib = len(whole) / (1 << 20)
     print(f"lz4 port, 1 thread, {mib:.1f} MiB: compress {mib / (t1 - t0):.0f} MiB/s, decompress {mib / (t2 - t1):.0f} MiB/s, ratio {len(c) / len(whole):.3f}")
+
+
+def test_xxh64_hash_long_equals_bytes(oracle):
+    # AbstractTestXxHash64.java:321-341: hash(long) == hash of its 8 little-endian bytes, with and without seed
+    PRIME32 = 0x9E3779B1
+    for v in (0x0102030405060708, 0, 12345, 0x7FFFFFFFFFFFFFFF, 0xDEADBEEFCAFEBABE):
+        for seed in (0, PRIME32):
+            assert oracle.xxh64_long(v, seed) == oracle.xxh64(v.to_bytes(8, "little"), seed)
