@@ -58,6 +58,32 @@ def best_thread_count(run_pass, max_threads):
     return best
 
 
+def time_native_cpu(orc, op, src, soff, slen, dst, doff, dcap, max_threads, unc_bytes, seconds=4.0):
+    """The reference's NATIVE CPU path (its bundled liblz4 / libsnappy / libzstd, which its factories prefer when natives are
+    enabled: lz4/Lz4Compressor.java:28-43) on the same sample, one call per block, OpenMP over blocks.  Reported beside the
+    port of the Java path; None when the library is not available."""
+    try:
+        from oracle.pyoracle import RefNative
+        ref = RefNative()
+        if ref.entry_point(op) is None:
+            return None
+        run = lambda t: orc.native_batch(op, ref, src, soff, slen, dst, doff, dcap, threads=t)
+        fails, _ = run(max_threads)
+        if fails:
+            return None
+        threads = best_thread_count(run, max_threads)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            run(threads)
+            reps += 1
+        dt = time.perf_counter() - t0
+        names = {0: "liblz4", 1: "liblz4", 2: "libsnappy", 3: "libsnappy", 4: "libzstd (level 3)", 5: "libzstd"}
+        return {"value": unc_bytes * reps / dt / GiB, "unit": "GiB/s", "cores": threads, "kind": "reference",
+                "lib": f"{names[op]} bundled by the reference (oracle/_ref), versions {ref.versions()}"}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "error": repr(ex)[:160]}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -184,16 +210,45 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = unc * args.steps / dt / GiB
     sample = f"{n_sample} blocks x {args.block_kib} KiB ({unc / GiB:.2f} GiB uncompressed) per step"
+    native = time_native_cpu(orc, op, src, soff, slen, dst, doff, dcap, host_threads(), unc) if args.op != "hash" else None
     line = {
         "impl": "reference", "metric": f"{args.codec}_{args.op}_uncompressed_GiB_per_s", "value": value, "unit": "GiB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": f"synthetic batch: {wl['label']}",
         "config": {"workload": f"{args.codec} block {args.op}, {args.block_kib} KiB blocks x {args.blocks} batch per GPU",
                    "note": "reference CPU algorithm (C restatement of the Java codec, oracle/), one call per block, OpenMP over blocks; thread count = fastest of N, N/2, N/4, N/8"},
-        "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": threads, "kind": "port", "sample": sample, "reference_native": native},
         "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(args, wl, orc, op, n, threads):
+    """cpu_baseline: the oracle port of the reference's Java path (and, beside it, the reference's native path) timed on this
+    host's cores on a bounded sample of the same workload, one call per block."""
+    ns = min(n, args.ref_blocks)
+    _, _, _, soff, slen = tile_index(wl["comp_off"] if args.op == "decompress" else wl["raw_off"],
+                                     wl["comp_len"] if args.op == "decompress" else wl["raw_len"], ns)
+    base = wl["comp"] if args.op == "decompress" else wl["raw"]
+    src = np.tile(np.pad(base, (0, ((len(base) + 255) & ~255) - len(base))), (ns + wl["distinct"] - 1) // wl["distinct"])
+    if args.op == "decompress":
+        _, _, _, doff, dcap = tile_index(wl["raw_off"], wl["raw_len"], ns)
+        unc_s = int(dcap.sum())
+    else:
+        b = orc.max_compressed_length(args.codec, int(slen.max()))
+        doff, dcap = np.arange(ns, dtype=np.int64) * b, np.full(ns, b, dtype=np.int64)
+        unc_s = int(slen.sum())
+    dst = np.zeros(int(doff[-1] + dcap[-1]), dtype=np.uint8)
+    cpu_threads = best_thread_count(lambda t: orc.batch(op, src, soff, slen, dst, doff, dcap, threads=t), threads)
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 8.0:
+        orc.batch(op, src, soff, slen, dst, doff, dcap, threads=cpu_threads)
+        reps += 1
+    dt = time.perf_counter() - t0
+    cpu_baseline = {"value": unc_s * reps / dt / GiB, "unit": "GiB/s", "cores": cpu_threads, "kind": "port",
+                    "sample": f"{ns} blocks x {args.block_kib} KiB x {reps} passes, {cpu_threads} of {threads} host threads (fastest of N, N/2, N/4, N/8), one call per block"}
+    cpu_baseline["reference_native"] = time_native_cpu(orc, op, src, soff, slen, dst, doff, dcap, threads, unc_s)
+    return cpu_baseline
 
 
 def main():
@@ -418,27 +473,10 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline and args.op != "hash":
-        ns = min(n, args.ref_blocks)
-        _, _, _, soff, slen = tile_index(wl["comp_off"] if args.op == "decompress" else wl["raw_off"],
-                                         wl["comp_len"] if args.op == "decompress" else wl["raw_len"], ns)
-        base = wl["comp"] if args.op == "decompress" else wl["raw"]
-        src = np.tile(np.pad(base, (0, ((len(base) + 255) & ~255) - len(base))), (ns + wl["distinct"] - 1) // wl["distinct"])
-        if args.op == "decompress":
-            _, _, _, doff, dcap = tile_index(wl["raw_off"], wl["raw_len"], ns)
-            unc_s = int(dcap.sum())
-        else:
-            b = orc.max_compressed_length(args.codec, int(slen.max()))
-            doff, dcap = np.arange(ns, dtype=np.int64) * b, np.full(ns, b, dtype=np.int64)
-            unc_s = int(slen.sum())
-        dst = np.zeros(int(doff[-1] + dcap[-1]), dtype=np.uint8)
-        cpu_threads = best_thread_count(lambda t: orc.batch(op, src, soff, slen, dst, doff, dcap, threads=t), threads)
-        reps, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < 8.0:
-            orc.batch(op, src, soff, slen, dst, doff, dcap, threads=cpu_threads)
-            reps += 1
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": unc_s * reps / dt / GiB, "unit": "GiB/s", "cores": cpu_threads, "kind": "port",
-                        "sample": f"{ns} blocks x {args.block_kib} KiB x {reps} passes, {cpu_threads} of {threads} host threads (fastest of N, N/2, N/4, N/8), one call per block"}
+        try:
+            cpu_baseline = cpu_baseline_leg(args, wl, orc, op, n, threads)
+        except Exception as ex:  # noqa: BLE001 -- never lose the GPU line because the CPU leg failed
+            cpu_baseline = {"value": None, "unit": "GiB/s", "cores": 0, "kind": "port", "sample": "failed", "error": repr(ex)[:200]}
 
     line = {
         "metric": f"{args.codec}_{args.op}_uncompressed_GiB_per_s", "value": value, "unit": "GiB/s", "n_gpus": world,

@@ -45,3 +45,40 @@ int64_t orc_batch(int32_t op, const uint8_t *src_base, const int64_t *src_off, c
     }
     return failures;
 }
+
+/*
+ * The same per-block loop over the reference's bundled NATIVE libraries (what Lz4Native / SnappyNative / ZstdNative bind,
+ * lz4/Lz4Native.java:97-146, snappy/SnappyNative.java:37-56, zstd/ZstdNative.java:108-163): `fn` is the address of
+ * LZ4_compress_fast / LZ4_decompress_safe / snappy_compress / snappy_uncompress / ZSTD_compress / ZSTD_decompress,
+ * resolved by the caller with dlopen (oracle/pyoracle.py RefNative).  Used by bench.py to report the reference's native
+ * CPU path next to the port of its Java path.  Returns the number of failed blocks.
+ */
+int64_t orc_native_batch(int32_t op, void *fn, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int64_t n, int32_t threads)
+{
+    typedef int (*lz4c_t)(const char *, char *, int, int, int);
+    typedef int (*lz4d_t)(const char *, char *, int, int);
+    typedef int (*snp_t)(const char *, size_t, char *, size_t *);
+    typedef size_t (*zc_t)(void *, size_t, const void *, size_t, int);
+    typedef size_t (*zd_t)(void *, size_t, const void *, size_t);
+    int64_t failures = 0;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads) reduction(+ : failures)
+    for (int64_t i = 0; i < n; i++) {
+        const char *s = (const char *) (src_base + src_off[i]);
+        char *d = (char *) (dst_base + dst_off[i]);
+        const int64_t cap = dst_cap[i];
+        int64_t r = -1;
+        switch (op) {
+            case 0: r = ((lz4c_t) fn)(s, d, (int) src_len[i], (int) cap, 1); if (r <= 0) r = -1; break;
+            case 1: r = ((lz4d_t) fn)(s, d, (int) src_len[i], (int) cap); break;
+            case 2: case 3: { size_t len = (size_t) cap; int st = ((snp_t) fn)(s, (size_t) src_len[i], d, &len); r = st == 0 ? (int64_t) len : -1; break; }
+            case 4: { size_t z = ((zc_t) fn)(d, (size_t) cap, s, (size_t) src_len[i], 3); r = z <= (size_t) cap ? (int64_t) z : -1; break; }
+            case 5: { size_t z = ((zd_t) fn)(d, (size_t) cap, s, (size_t) src_len[i]); r = z <= (size_t) cap ? (int64_t) z : -1; break; }
+            default: break;
+        }
+        out_len[i] = r;
+        if (r < 0) failures++;
+    }
+    return failures;
+}

@@ -83,6 +83,9 @@ int64_t orc_zstd_decompressed_size(const uint8_t *in, int64_t in_len, int64_t *e
 int64_t orc_batch(int32_t op, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
                   uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap,
                   int64_t *out_len, int64_t n, int32_t threads);
+/* same loop over the reference's bundled native libraries; fn = address of the native entry point for `op` (see batch_oracle.c) */
+int64_t orc_native_batch(int32_t op, void *fn, const uint8_t *src_base, const int64_t *src_off, const int64_t *src_len,
+                         uint8_t *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int64_t n, int32_t threads);
 int32_t orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -51,6 +51,8 @@ class Oracle:
         L.orc_xxh64_long.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_batch.restype = i64
         L.orc_batch.argtypes = [C.c_int32, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
+        L.orc_native_batch.restype = i64
+        L.orc_native_batch.argtypes = [C.c_int32, C.c_void_p, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
         L.orc_max_threads.restype = C.c_int32
 
     def max_compressed_length(self, codec, n):
@@ -100,6 +102,23 @@ class Oracle:
             dst.ctypes.data_as(p8) if dst is not None else None,
             dst_off.ctypes.data_as(pi64) if dst_off is not None else None,
             dst_cap.ctypes.data_as(pi64) if dst_cap is not None else None,
+            out_len.ctypes.data_as(pi64), n, threads)
+        return fails, out_len
+
+
+    def native_batch(self, op, ref, src, src_off, src_len, dst, dst_off, dst_cap, threads=1):
+        """The same per-block loop over the reference's bundled native library (ref = RefNative()); ops 0..5 only.
+        Returns (failures, out_len array), or None when that library is not available."""
+        fn = ref.entry_point(op)
+        if fn is None:
+            return None
+        n = len(src_off)
+        out_len = np.zeros(n, dtype=np.int64)
+        pi64 = C.POINTER(C.c_int64)
+        p8 = C.POINTER(C.c_uint8)
+        fails = self.lib.orc_native_batch(
+            op, fn, src.ctypes.data_as(p8), src_off.ctypes.data_as(pi64), src_len.ctypes.data_as(pi64),
+            dst.ctypes.data_as(p8), dst_off.ctypes.data_as(pi64), dst_cap.ctypes.data_as(pi64),
             out_len.ctypes.data_as(pi64), n, threads)
         return fails, out_len
 
@@ -166,6 +185,29 @@ class RefNative:
     @staticmethod
     def _ptr(a):
         return a.ctypes.data_as(C.c_void_p)
+
+    def entry_point(self, op):
+        """address of the native function behind batch op 0..5 (lz4 c/d, snappy c/d, zstd c/d), or None"""
+        table = {0: (self.lz4, "LZ4_compress_fast"), 1: (self.lz4, "LZ4_decompress_safe"), 2: (self.snappy, "snappy_compress"),
+                 3: (self.snappy, "snappy_uncompress"), 4: (self.zstd, "ZSTD_compress"), 5: (self.zstd, "ZSTD_decompress")}
+        lib, name = table.get(op, (None, None))
+        if lib is None:
+            return None
+        return C.cast(getattr(lib, name), C.c_void_p).value
+
+    def versions(self):
+        out = {}
+        try:
+            self.lz4.LZ4_versionString.restype = C.c_char_p
+            out["lz4"] = self.lz4.LZ4_versionString().decode()
+        except Exception:
+            pass
+        try:
+            self.zstd.ZSTD_versionString.restype = C.c_char_p
+            out["zstd"] = self.zstd.ZSTD_versionString().decode()
+        except Exception:
+            pass
+        return out
 
     def compress(self, codec, data, level=3):
         src = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
