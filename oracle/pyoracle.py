@@ -51,8 +51,11 @@ class Oracle:
         L.orc_xxh64_long.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_batch.restype = i64
         L.orc_batch.argtypes = [C.c_int32, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
-        L.orc_native_batch.restype = i64
-        L.orc_native_batch.argtypes = [C.c_int32, C.c_void_p, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
+        try:   # absent from a liboracle.so built before this entry point existed
+            L.orc_native_batch.restype = i64
+            L.orc_native_batch.argtypes = [C.c_int32, C.c_void_p, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
+        except AttributeError:
+            pass
         L.orc_max_threads.restype = C.c_int32
 
     def max_compressed_length(self, codec, n):
@@ -110,7 +113,7 @@ class Oracle:
         """The same per-block loop over the reference's bundled native library (ref = RefNative()); ops 0..5 only.
         Returns (failures, out_len array), or None when that library is not available."""
         fn = ref.entry_point(op)
-        if fn is None:
+        if fn is None or not hasattr(self.lib, "orc_native_batch"):
             return None
         n = len(src_off)
         out_len = np.zeros(n, dtype=np.int64)
