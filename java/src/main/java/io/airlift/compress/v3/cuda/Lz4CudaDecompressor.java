@@ -1,0 +1,66 @@
+package io.airlift.compress.v3.cuda;
+
+import io.airlift.compress.v3.Decompressor;
+import io.airlift.compress.v3.MalformedInputException;
+
+import java.lang.foreign.MemorySegment;
+
+import static java.lang.String.format;
+
+/**
+ * LZ4 block decompressor on the GPU: accepts and rejects exactly what Lz4JavaDecompressor does (same messages and offsets).
+ * Implements the plain {@link Decompressor} interface (the codec-specific interfaces of the reference are sealed), one CUDA
+ * context per instance; not thread-safe, like the reference's codec objects.
+ */
+public final class Lz4CudaDecompressor
+        implements Decompressor, AutoCloseable
+{
+    private final CudaContext context;
+
+    public Lz4CudaDecompressor()
+    {
+        this(0);
+    }
+
+    public Lz4CudaDecompressor(int device)
+    {
+        this.context = new CudaContext(device);
+    }
+
+    public static boolean isEnabled()
+    {
+        return AircompressCuda.isEnabled();
+    }
+
+    @Override
+    public int decompress(byte[] input, int inputOffset, int inputLength, byte[] output, int outputOffset, int maxOutputLength)
+            throws MalformedInputException
+    {
+        verifyRange(input, inputOffset, inputLength);
+        verifyRange(output, outputOffset, maxOutputLength);
+        return context.call(AircompressCuda.OP_LZ4_DECOMPRESS,
+                MemorySegment.ofArray(input).asSlice(inputOffset, inputLength), inputLength,
+                MemorySegment.ofArray(output).asSlice(outputOffset, maxOutputLength), maxOutputLength);
+    }
+
+    @Override
+    public int decompress(MemorySegment input, MemorySegment output)
+            throws MalformedInputException
+    {
+        return context.call(AircompressCuda.OP_LZ4_DECOMPRESS, input, input.byteSize(), output, output.byteSize());
+    }
+
+    private static void verifyRange(byte[] data, int offset, int length)
+    {
+        java.util.Objects.requireNonNull(data, "data is null");
+        if (offset < 0 || length < 0 || offset + length > data.length) {
+            throw new IllegalArgumentException(format("Invalid offset or length (%s, %s) in array of length %s", offset, length, data.length));
+        }
+    }
+
+    @Override
+    public void close()
+    {
+        context.close();
+    }
+}

@@ -1,0 +1,70 @@
+package io.airlift.compress.v3.cuda;
+
+import io.airlift.compress.v3.Compressor;
+
+import java.lang.foreign.MemorySegment;
+
+import static java.lang.Math.toIntExact;
+import static java.lang.String.format;
+
+/**
+ * Zstandard frame compressor on the GPU (one frame per call, checksum always set, like ZstdJavaCompressor).
+ * Implements the plain {@link Compressor} interface (the codec-specific interfaces of the reference are sealed), one CUDA
+ * context per instance; not thread-safe, like the reference's codec objects.
+ */
+public final class ZstdCudaCompressor
+        implements Compressor, AutoCloseable
+{
+    private final CudaContext context;
+
+    public ZstdCudaCompressor()
+    {
+        this(0);
+    }
+
+    public ZstdCudaCompressor(int device)
+    {
+        this.context = new CudaContext(device);
+    }
+
+    public static boolean isEnabled()
+    {
+        return AircompressCuda.isEnabled();
+    }
+
+    @Override
+    public int maxCompressedLength(int uncompressedSize)
+    {
+        return toIntExact(AircompressCuda.bound(AircompressCuda.OP_ZSTD_COMPRESS, uncompressedSize));
+    }
+
+    @Override
+    public int compress(byte[] input, int inputOffset, int inputLength, byte[] output, int outputOffset, int maxOutputLength)
+    {
+        verifyRange(input, inputOffset, inputLength);
+        verifyRange(output, outputOffset, maxOutputLength);
+        return context.call(AircompressCuda.OP_ZSTD_COMPRESS,
+                MemorySegment.ofArray(input).asSlice(inputOffset, inputLength), inputLength,
+                MemorySegment.ofArray(output).asSlice(outputOffset, maxOutputLength), maxOutputLength);
+    }
+
+    @Override
+    public int compress(MemorySegment input, MemorySegment output)
+    {
+        return context.call(AircompressCuda.OP_ZSTD_COMPRESS, input, input.byteSize(), output, output.byteSize());
+    }
+
+    private static void verifyRange(byte[] data, int offset, int length)
+    {
+        java.util.Objects.requireNonNull(data, "data is null");
+        if (offset < 0 || length < 0 || offset + length > data.length) {
+            throw new IllegalArgumentException(format("Invalid offset or length (%s, %s) in array of length %s", offset, length, data.length));
+        }
+    }
+
+    @Override
+    public void close()
+    {
+        context.close();
+    }
+}

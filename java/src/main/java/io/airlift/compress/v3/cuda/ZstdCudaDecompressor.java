@@ -1,0 +1,73 @@
+package io.airlift.compress.v3.cuda;
+
+import io.airlift.compress.v3.Decompressor;
+import io.airlift.compress.v3.MalformedInputException;
+
+import java.lang.foreign.MemorySegment;
+
+import static java.lang.String.format;
+
+/**
+ * Zstandard decompressor on the GPU (concatenated frames, checksum verification): accepts and rejects what ZstdJavaDecompressor does.
+ * Implements the plain {@link Decompressor} interface (the codec-specific interfaces of the reference are sealed), one CUDA
+ * context per instance; not thread-safe, like the reference's codec objects.
+ */
+public final class ZstdCudaDecompressor
+        implements Decompressor, AutoCloseable
+{
+    private final CudaContext context;
+
+    public ZstdCudaDecompressor()
+    {
+        this(0);
+    }
+
+    public ZstdCudaDecompressor(int device)
+    {
+        this.context = new CudaContext(device);
+    }
+
+    public static boolean isEnabled()
+    {
+        return AircompressCuda.isEnabled();
+    }
+
+    @Override
+    public int decompress(byte[] input, int inputOffset, int inputLength, byte[] output, int outputOffset, int maxOutputLength)
+            throws MalformedInputException
+    {
+        verifyRange(input, inputOffset, inputLength);
+        verifyRange(output, outputOffset, maxOutputLength);
+        return context.call(AircompressCuda.OP_ZSTD_DECOMPRESS,
+                MemorySegment.ofArray(input).asSlice(inputOffset, inputLength), inputLength,
+                MemorySegment.ofArray(output).asSlice(outputOffset, maxOutputLength), maxOutputLength);
+    }
+
+    @Override
+    public int decompress(MemorySegment input, MemorySegment output)
+            throws MalformedInputException
+    {
+        return context.call(AircompressCuda.OP_ZSTD_DECOMPRESS, input, input.byteSize(), output, output.byteSize());
+    }
+
+    /** ZstdDecompressor.getDecompressedSize: the content size of the first frame, -1 when it is not recorded */
+    public long getDecompressedSize(byte[] input, int offset, int length)
+    {
+        verifyRange(input, offset, length);
+        return AircompressCuda.zstdFrameContentSize(MemorySegment.ofArray(input).asSlice(offset, length), length);
+    }
+
+    private static void verifyRange(byte[] data, int offset, int length)
+    {
+        java.util.Objects.requireNonNull(data, "data is null");
+        if (offset < 0 || length < 0 || offset + length > data.length) {
+            throw new IllegalArgumentException(format("Invalid offset or length (%s, %s) in array of length %s", offset, length, data.length));
+        }
+    }
+
+    @Override
+    public void close()
+    {
+        context.close();
+    }
+}
