@@ -65,3 +65,27 @@ def test_partition_by_bytes():
         assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
     even = sharding.partition_by_bytes(np.full(65536, 65536), 8)
     assert [e - b for b, e in even] == [8192] * 8
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/aircompress_cuda.h is the contract a cgo / JNI / FFM host binds: it must compile as strict C99 (and as C++),
+    and a plain-C consumer (examples/acc_roundtrip.c) must compile warning-free and link against the library.  Without a GPU
+    the program must fail loudly at acc_init (exit code 2), never fall back."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "aircompress_cuda.h"\nint main(void) { return acc_lz4_compress_bound(0) == 16 ? 0 : 1; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(probe)], check=True)
+    subprocess.run([shutil.which("g++") or "/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(probe)], check=True)
+    exe = tmp_path / "acc_roundtrip"
+    libdir = os.path.join(root, "aircompressor_b200")
+    subprocess.run([gcc, "-O2", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", inc, os.path.join(root, "examples", "acc_roundtrip.c"),
+                    "-L", libdir, "-laircompress_cuda", "-o", str(exe)], check=True)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(exe), os.path.join(root, "README.md")], env=dict(os.environ, LD_LIBRARY_PATH=libdir), capture_output=True, text=True)
+        assert r.returncode == 2 and "acc_init failed" in r.stderr
