@@ -27,8 +27,18 @@ def refnative():
 
 @pytest.fixture(scope="session")
 def pieces():
+    """the committed 1/24 stratified sample (small, for the quick parity cases)"""
     import benchdata
-    return benchdata.load_pieces()[1]
+    return benchdata.load_pieces(sample=True)[1]
+
+
+@pytest.fixture(scope="session")
+def corpus_files():
+    """all 12 files of the Silesia corpus (unpacked on first use from data/silesia_xz/)"""
+    import benchdata
+    label, files = benchdata.load_pieces()
+    assert "full corpus" in label, "data/silesia_xz is missing from the tree"
+    return files
 
 
 @pytest.fixture(scope="session")
