@@ -27,7 +27,7 @@ struct acc_ctx {
     int64_t last_offset = 0;
     int64_t launches = 0;
     int tuning_ctas_per_sm = 0;
-    int tuning_decoder = 0;   // 0 = default, 1 = warp-per-block (v1), 3 = shared-memory window (v3)
+    int tuning_decoder = 0;   // LZ4/Snappy decode kernel: 0 = default, 1 = warp-per-block step decoder, 2 = streaming engine (lz_stream.cuh)
     int tuning_pipeline = 0;  // host-pointer batches: 0 = auto, 1 = never split, k > 1 = split into k chunks
     // copy streams + events of the pipelined host-pointer path (created on first use)
     static constexpr int kMaxChunks = 16;
@@ -115,7 +115,6 @@ int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
     if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
     if (key == 1) { int prev = c->tuning_decoder; c->tuning_decoder = value; return prev; }
     if (key == 3) { int prev = c->tuning_pipeline; c->tuning_pipeline = value; return prev; }
-    if (key == 2) { extern int g_tpb_max_ctas; int prev = g_tpb_max_ctas; g_tpb_max_ctas = value; return prev; }
     return 0;
 }
 

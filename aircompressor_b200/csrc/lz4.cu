@@ -7,6 +7,8 @@
 // AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
 #include "lz4_decode_v1.cuh"
+#include "lz_stream.cuh"
+#include "lz4_stream.cuh"
 
 namespace {
 
@@ -25,6 +27,18 @@ __global__ void __launch_bounds__(256, kMinCtas) lz4_decompress_kernel(AccBatch 
         lz4_decode_block<kFast>(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
                                 b.out_len, b.status, idx, lane);
     }
+}
+
+constexpr int kLz4StreamSlots = 31;   // execute warps (= blocks in flight) per CTA; + 1 parse warp = 1024 threads, one CTA per SM
+
+__global__ void __launch_bounds__((kLz4StreamSlots + 1) * 32, 1) lz4_stream_decompress_kernel(AccBatch b)
+{
+    extern __shared__ __align__(128) uint8_t lzs_smem[];
+    lzs::Slot *slots = reinterpret_cast<lzs::Slot *>(lzs_smem);
+    if (threadIdx.x < kLz4StreamSlots) lzs::init_slot(slots[threadIdx.x]);
+    lzs::fence_proxy_async();
+    __syncthreads();
+    lzs::run_warp<Lz4Stream, kLz4StreamSlots>(b, slots, threadIdx.x >> 5, lane_id());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,26 +200,26 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
 
 }  // namespace
 
-void acc_launch_lz4_decompress_v3(const AccBatch &b, int sm_count, cudaStream_t st);    // lz4_v3.cu
-void acc_launch_lz4_decompress_tpb(const AccBatch &b, int sm_count, cudaStream_t st);   // lz4_tpb.cu
-
 void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
-    if (version == 3) { acc_launch_lz4_decompress_v3(b, sm_count, st); return; }
-    if (version == 2) { acc_launch_lz4_decompress_tpb(b, sm_count, st); return; }
+    if (version == 0 || version == 2) {
+        // streaming engine: one CTA per SM, 31 blocks in flight per CTA
+        const int smem = kLz4StreamSlots * (int) sizeof(lzs::Slot);
+        cudaFuncSetAttribute(lz4_stream_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int64_t ctas = (b.n + kLz4StreamSlots - 1) / kLz4StreamSlots;
+        if (ctas > sm_count) ctas = sm_count;
+        if (ctas < 1) ctas = 1;
+        lz4_stream_decompress_kernel<<<(unsigned) ctas, (kLz4StreamSlots + 1) * 32, smem, st>>>(b);
+        return;
+    }
+    // version 1: warp-per-block step decoder (round 1): multi-sequence + medium steps, registers bounded for 8 resident
+    // CTAs (32 registers, 64 warps per SM)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
-    int64_t warps_needed = b.n;
-    int64_t ctas = (warps_needed + 7) / 8;
+    int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    // default: multi-sequence + medium steps, registers bounded for 8 resident CTAs (32 registers, 64 warps per SM):
-    // 253 GiB/s vs 248 (6 CTAs, 40 registers) and ~200 (unbounded: 63 registers, 4 CTAs) on the bench batch
-    if (version == 4) lz4_decompress_kernel<1, 1><<<(unsigned) ctas, 256, 0, st>>>(b);        // one sequence per step (first round-1 kernel)
-    else if (version == 5) lz4_decompress_kernel<2, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // multi-sequence steps only
-    else if (version == 6) lz4_decompress_kernel<3, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else if (version == 8) lz4_decompress_kernel<3, 1><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else lz4_decompress_kernel<3, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
+    lz4_decompress_kernel<3, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter)

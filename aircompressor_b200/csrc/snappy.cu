@@ -5,214 +5,12 @@
 // the Java decoder (same accept/reject decisions and error offsets); encode emits a valid stream the
 // Java decoder round-trips (AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
+#include "lz_stream.cuh"
+#include "snappy_decode.cuh"
 
 namespace {
 
-// SnappyRawDecompressor.java:238-271 opLookupTable as a formula: bits 0-7 length, 8-10 offset/256,
-// 11-13 trailer bytes.
-__device__ __forceinline__ uint32_t snappy_op_entry(uint32_t op)
-{
-    uint32_t kind = op & 3, hi = op >> 2;
-    if (kind == 0) return hi < 60 ? hi + 1 : (((hi - 59) << 11) | 1);
-    if (kind == 1) return (1u << 11) | ((op >> 5) << 8) | (4 + (hi & 7));
-    if (kind == 2) return (2u << 11) | (hi + 1);
-    return (4u << 11) | (hi + 1);
-}
-
-// Java readUncompressedLength (SnappyRawDecompressor.java:277-321). Returns status word (0 = ok).
-__device__ __forceinline__ int32_t snappy_read_length(const uint8_t *in, int64_t in_len, uint32_t *result_out, int *bytes_read, int64_t *err_off)
-{
-    uint32_t result = 0;
-    int n = 0;
-    for (int shift = 0;; shift += 7) {
-        if (n >= in_len) { *err_off = in_len - n; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_TRUNCATED); }
-        uint32_t b = in[n++];
-        result |= (b & 0x7f) << shift;
-        if (!(b & 0x80)) break;
-        if (shift == 28) { *err_off = n; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_VARINT_HIGHBIT); }
-    }
-    if ((int32_t) result < 0) { *err_off = 0; return ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_NEG_LENGTH); }
-    *result_out = result;
-    *bytes_read = n;
-    return 0;
-}
-
-// kMulti: try multi-element steps (up to four elements per warp step) before the pair path.
-template <bool kMulti>
-__device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ in0, int64_t in_len0, uint8_t *out, int64_t out_cap,
-                                                    int64_t *out_len, int32_t *status, int lane)
-{
-#define SN_FAIL(off) do { if (lane == 0) { *out_len = (off); *status = ACC_STATUS(ACC_E_MALFORMED, ACC_R_NONE); } return; } while (0)
-    uint32_t expected = 0;
-    int br = 0;
-    int64_t eoff = 0;
-    int32_t st = snappy_read_length(in0, in_len0, &expected, &br, &eoff);
-    if (st != 0) { if (lane == 0) { *out_len = eoff; *status = st; } return; }
-    if ((int64_t) expected > out_cap) {
-        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_DST_TOO_SMALL, ACC_R_SNAPPY_LEN_GT_CAP); }
-        return;
-    }
-    // base pointers made opaque so the compiler keeps the two 64-bit sums in registers (see lz4_decode_v1.cuh)
-    const uint8_t *in = in0 + br;
-    asm volatile("" : "+l"(in));
-    asm volatile("" : "+l"(out));
-    __builtin_assume(__isGlobal(in));
-    __builtin_assume(__isGlobal(out));
-    const int64_t in_len = in_len0 - br;
-    const int64_t fast_output_limit = out_cap - 8;
-    int64_t ip = 0, op = 0;
-
-    const bool small = in_len < 0x7fffff00LL && out_cap < 0x7fffff00LL;
-    // multi-element steps run while ip <= ip_lim && op <= op_lim (-1: never)
-    const int32_t ip_lim = (kMulti && small && in_len >= 32 && out_cap >= 32) ? (int32_t) in_len - 32 : -1;
-    const int32_t op_lim = (kMulti && small && in_len >= 32 && out_cap >= 32) ? (int32_t) out_cap - 32 : -1;
-    while (ip < in_len) {
-        if (kMulti) {
-            uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
-            while ((int32_t) ipw <= ip_lim && (int32_t) opw <= op_lim) {
-                const uint32_t vb = __ldg(in + (ipw + (uint32_t) lane));
-                // ---- multi-element step: up to four elements (literals of < 32 bytes, 1- and 2-byte-offset copies) that
-                // lie completely in the 32-byte window and produce at most 32 bytes together.  Every lane first decodes
-                // ITS byte as if it were a tag (output bytes, input bytes, offset), the warp follows the chain
-                // tag -> next tag with two shuffles per element, and every lane resolves the source of one output byte:
-                // a literal of the window, older output (one global load), or a byte another lane produces in this step
-                // (taken by shuffle once that lane has it; dependencies point to lower lanes).  An element is only taken
-                // when it is valid under SnappyRawDecompressor.java:89-216 (offset != 0, offset <= op, output fits);
-                // anything else ends the chain and is left to the paths below, which report errors at the same offsets.
-                const uint32_t kind = vb & 3, hi = vb >> 2;
-                const uint32_t b1 = __shfl_sync(kFull, vb, lane + 1), b2 = __shfl_sync(kFull, vb, lane + 2);
-                uint32_t outn = hi + 1, adv = 3, off = b1 | (b2 << 8);                  // 2-byte-offset copy
-                if (kind == 1) { outn = 4 + (hi & 7); adv = 2; off = ((vb >> 5) << 8) | b1; }
-                if (kind == 0) { adv = hi + 2; off = 0; }                               // literal: offset 0 marks it
-                const bool usable = kind != 3 && !(kind == 0 && hi >= 60) && !(kind != 0 && off == 0) && (uint32_t) lane + adv <= 32 && outn <= 32;
-                const uint32_t A = (usable ? outn : 127u) | ((adv & 63) << 8);
-                const uint32_t a0 = __shfl_sync(kFull, A, 0), o0 = __shfl_sync(kFull, off, 0);
-                const uint32_t n0 = a0 & 127, x1 = a0 >> 8;
-                const bool ok0 = n0 <= 32 && o0 <= opw;                                // copies: 1 <= offset <= op (0 = literal)
-                const uint32_t a1 = __shfl_sync(kFull, A, x1), o1 = __shfl_sync(kFull, off, x1);
-                const uint32_t e1 = n0 + (a1 & 127), x2 = x1 + (a1 >> 8);
-                const bool v1 = ok0 && x1 < 32 && e1 <= 32 && o1 <= opw + n0;
-                if (!v1) break;
-                {
-                    const uint32_t a2 = __shfl_sync(kFull, A, x2), o2 = __shfl_sync(kFull, off, x2);
-                    const uint32_t e2 = e1 + (a2 & 127), x3 = x2 + (a2 >> 8);
-                    const bool v2 = x2 < 32 && e2 <= 32 && o2 <= opw + e1;
-                    const uint32_t a3 = __shfl_sync(kFull, A, x3), o3 = __shfl_sync(kFull, off, x3);
-                    const uint32_t e3 = e2 + (a3 & 127), x4 = x3 + (a3 >> 8);
-                    const bool v3 = v2 && x3 < 32 && e3 <= 32 && o3 <= opw + e2;
-                    const uint32_t e = v3 ? e3 : v2 ? e2 : e1;                          // output bytes of this step
-                    const uint32_t nx = v3 ? x4 : v2 ? x3 : x2;                         // input bytes of this step
-                    // which element produces output byte `lane`
-                    const bool k3 = v3 && (uint32_t) lane >= e2, k2 = v2 && (uint32_t) lane >= e1, k1 = (uint32_t) lane >= n0;
-                    const uint32_t sk = k3 ? x3 : k2 ? x2 : k1 ? x1 : 0u;               // tag position in the window
-                    const uint32_t bk = k3 ? e2 : k2 ? e1 : k1 ? n0 : 0u;               // first output byte of the element
-                    const uint32_t fk = k3 ? o3 : k2 ? o2 : k1 ? o1 : o0;               // offset (0: literal)
-                    const uint32_t t = (uint32_t) lane - bk;
-                    uint32_t val = __shfl_sync(kFull, vb, sk + 1 + t);                  // the literal byte, if it is one
-                    uint32_t m = t;
-                    if (fk != 0 && m >= fk) m -= fk * ((m * kRcp16[fk]) >> 16);         // m mod offset (offset < 32 here)
-                    const int32_t srel = (int32_t) (bk + m) - (int32_t) fk;             // source, relative to op
-                    uint32_t need = ((uint32_t) lane < e && fk != 0) ? 256u : 0u;
-                    if (need && srel < 0) { val = out[opw + (uint32_t) srel]; need = 0; }   // opw + srel >= 0 (offsets checked)
-                    while (__any_sync(kFull, need)) {
-                        const uint32_t w = __shfl_sync(kFull, val | need, srel);
-                        if (need && !(w & 256u)) { val = w; need = 0; }
-                    }
-                    if ((uint32_t) lane < e) out[opw + lane] = (uint8_t) val;
-                    __syncwarp();
-                    ipw += nx;
-                    opw += e;
-                }
-            }
-            ip = ipw;
-            op = opw;
-            if (ip >= in_len) break;
-        }
-        // ---- fast path: [literal of <= 27 bytes] + [one 1- or 2-byte-offset copy], parsed from one coalesced 32-byte load.
-        // Every output byte is resolved independently (a literal byte of this step, or older output through the periodic
-        // source formula), so the step is one load and one store per lane and 32-byte chunk.  The bounds make the elements
-        // valid under SnappyRawDecompressor.java:89-216; anything else goes to the element-by-element path below.
-        if (small && ip + 32 <= in_len) {
-            const uint32_t ipw = (uint32_t) ip, opw = (uint32_t) op;
-            const uint32_t vb = __ldg(in + ipw + lane);
-            const uint32_t t0 = __shfl_sync(kFull, vb, 0);
-            uint32_t L = 0, p = 0;
-            bool ok = true;
-            if ((t0 & 3) == 0) {
-                const uint32_t n = t0 >> 2;
-                if (n <= 26) { L = n + 1; p = 1 + L; } else ok = false;
-            }
-            if (ok) {
-                const uint32_t tag = __shfl_sync(kFull, vb, p);
-                const uint32_t b1 = __shfl_sync(kFull, vb, (p + 1) & 31), b2 = __shfl_sync(kFull, vb, (p + 2) & 31);
-                const uint32_t kind = tag & 3;
-                uint32_t clen = 0, coff = 1, adv = p;
-                if (kind == 1) { clen = 4 + ((tag >> 2) & 7); coff = ((tag >> 5) << 8) | b1; adv = p + 2; }
-                else if (kind == 2) { clen = (tag >> 2) + 1; coff = b1 | (b2 << 8); adv = p + 3; }
-                else if (L == 0) ok = false;          // long literal / 4-byte-offset copy first: slow path
-                const uint32_t total = L + clen;
-                if (ok && coff != 0 && coff <= opw + L && (uint64_t) opw + total <= (uint64_t) out_cap) {
-                    for (uint32_t c = 0; c < total; c += 32) {
-                        const uint32_t j = c + lane;
-                        int32_t rel = (int32_t) j;     // position relative to op of the byte to copy (literal: itself, from the window)
-                        if (j >= L) {
-                            uint32_t m = j - L;
-                            if (m >= coff) m = m % coff;
-                            rel = (int32_t) L - (int32_t) coff + (int32_t) m;
-                        }
-                        uint32_t v = __shfl_sync(kFull, vb, (rel + 1) & 31);
-                        if (j < total) {
-                            if (rel < 0) v = out[(int64_t) opw + rel];
-                            out[opw + j] = (uint8_t) v;
-                        }
-                    }
-                    __syncwarp();
-                    ip = ipw + adv;
-                    op = opw + total;
-                    continue;
-                }
-            }
-        }
-        const uint32_t opc = in[ip++];
-        const uint32_t entry = snappy_op_entry(opc);
-        const int trailer_bytes = (int) (entry >> 11);
-        if (!(ip + 4 < in_len)) {
-            if (ip + trailer_bytes > in_len) SN_FAIL(ip);
-        }
-        uint32_t trailer = 0;
-        for (int i = trailer_bytes - 1; i >= 0; i--) trailer = (trailer << 8) | in[ip + i];
-        if ((int32_t) trailer < 0) SN_FAIL(ip);
-        ip += trailer_bytes;
-        const uint32_t length = entry & 0xff;
-
-        if ((opc & 3) == 0) {
-            const uint32_t ll = length + trailer;
-            if ((int32_t) ll < 0) SN_FAIL(ip);
-            const int64_t lit_out_limit = op + (int64_t) ll;
-            if (lit_out_limit > fast_output_limit || ip + (int64_t) ll > in_len - 8) {
-                if (lit_out_limit > out_cap || ip + (int64_t) ll > in_len) SN_FAIL(ip);
-            }
-            warp_copy(out + op, in + ip, ll, lane);
-            ip += ll;
-            op = lit_out_limit;
-        }
-        else {
-            const uint32_t moff = (entry & 0x700) + trailer;
-            if ((int32_t) moff <= 0) SN_FAIL(ip);
-            if ((int64_t) moff > op || op + (int64_t) length > out_cap) SN_FAIL(ip);
-            __syncwarp();
-            warp_match_copy(out + op, moff, length, lane);
-            __syncwarp();
-            op += length;
-        }
-    }
-    if ((int64_t) expected != op) {
-        if (lane == 0) { *out_len = 0; *status = ACC_STATUS(ACC_E_MALFORMED, ACC_R_SNAPPY_LEN_MISMATCH); }
-        return;
-    }
-    if (lane == 0) { *out_len = expected; *status = 0; }
-#undef SN_FAIL
-}
+using namespace snappydec;
 
 template <bool kMulti, int kMinCtas>
 __global__ void __launch_bounds__(256, kMinCtas) snappy_decompress_kernel(AccBatch b)
@@ -226,6 +24,18 @@ __global__ void __launch_bounds__(256, kMinCtas) snappy_decompress_kernel(AccBat
         snappy_decode_block<kMulti>(b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx],
                             b.out_len + idx, b.status + idx, lane);
     }
+}
+
+constexpr int kSnStreamSlots = 31;
+
+__global__ void __launch_bounds__((kSnStreamSlots + 1) * 32, 1) snappy_stream_decompress_kernel(AccBatch b)
+{
+    extern __shared__ __align__(128) uint8_t lzs_smem[];
+    lzs::Slot *slots = reinterpret_cast<lzs::Slot *>(lzs_smem);
+    if (threadIdx.x < kSnStreamSlots) lzs::init_slot(slots[threadIdx.x]);
+    lzs::fence_proxy_async();
+    __syncthreads();
+    lzs::run_warp<SnappyStream, kSnStreamSlots>(b, slots, threadIdx.x >> 5, lane_id());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,15 +189,23 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
 
 void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
+    if (version == 0 || version == 2) {
+        // streaming engine: one CTA per SM, 31 blocks in flight per CTA
+        const int smem = kSnStreamSlots * (int) sizeof(lzs::Slot);
+        cudaFuncSetAttribute(snappy_stream_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int64_t ctas = (b.n + kSnStreamSlots - 1) / kSnStreamSlots;
+        if (ctas > sm_count) ctas = sm_count;
+        if (ctas < 1) ctas = 1;
+        snappy_stream_decompress_kernel<<<(unsigned) ctas, (kSnStreamSlots + 1) * 32, smem, st>>>(b);
+        return;
+    }
+    // version 1: warp-per-block step decoder (round 1)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    if (version == 4) snappy_decompress_kernel<false, 1><<<(unsigned) ctas, 256, 0, st>>>(b);   // pair steps only (first round-1 kernel)
-    else if (version == 6) snappy_decompress_kernel<true, 6><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else if (version == 7) snappy_decompress_kernel<true, 8><<<(unsigned) ctas, 256, 0, st>>>(b);
-    else snappy_decompress_kernel<true, 5><<<(unsigned) ctas, 256, 0, st>>>(b);
+    snappy_decompress_kernel<true, 5><<<(unsigned) ctas, 256, 0, st>>>(b);
 }
 
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st)

@@ -41,9 +41,10 @@ def _gpu_decompress(engine, codec, streams, caps, guard=0):
     return dst, do, out_len, status
 
 
-@pytest.fixture(params=[1, 2, 3, 4, 5], ids=["warp-per-block", "thread-per-block", "smem-window", "warp-single-seq", "warp-multi-seq"])
+@pytest.fixture(params=[2, 1], ids=["stream-engine", "warp-step"])
 def decoder(request, engine):
-    """runs the decode tests against both LZ4 decoder kernels (tuning key 1)"""
+    """runs the decode tests against both LZ4 / Snappy decoder kernels (tuning key 1): the streaming engine (lz_stream.cuh,
+    the default) and the warp-per-block step decoder of round 1"""
     engine.set_tuning(1, request.param)
     yield request.param
     engine.set_tuning(1, 0)
