@@ -29,16 +29,13 @@ __global__ void __launch_bounds__(256, kMinCtas) lz4_decompress_kernel(AccBatch 
     }
 }
 
-constexpr int kLz4StreamSlots = 31;   // execute warps (= blocks in flight) per CTA; + 1 parse warp = 1024 threads, one CTA per SM
+constexpr int kStreamWarps = 8;        // warps per CTA of the two-phase decoder
+constexpr int kStreamCtasPerSm = 4;    // 32 warps per SM, each owning up to 32 blocks
 
-__global__ void __launch_bounds__((kLz4StreamSlots + 1) * 32, 1) lz4_stream_decompress_kernel(AccBatch b)
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) lz4_stream_decompress_kernel(AccBatch b, int lanes_in_use)
 {
-    extern __shared__ __align__(128) uint8_t lzs_smem[];
-    lzs::Slot *slots = reinterpret_cast<lzs::Slot *>(lzs_smem);
-    if (threadIdx.x < kLz4StreamSlots) lzs::init_slot(slots[threadIdx.x]);
-    lzs::fence_proxy_async();
-    __syncthreads();
-    lzs::run_warp<Lz4Stream, kLz4StreamSlots>(b, slots, threadIdx.x >> 5, lane_id());
+    __shared__ lzs::WarpSmem sm[kStreamWarps];
+    lzs::run_warp<Lz4Stream>(b, sm[threadIdx.x >> 5], lane_id(), lanes_in_use);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -203,13 +200,16 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
 void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
     if (version == 0 || version == 2) {
-        // streaming engine: one CTA per SM, 31 blocks in flight per CTA
-        const int smem = kLz4StreamSlots * (int) sizeof(lzs::Slot);
-        cudaFuncSetAttribute(lz4_stream_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        int64_t ctas = (b.n + kLz4StreamSlots - 1) / kLz4StreamSlots;
-        if (ctas > sm_count) ctas = sm_count;
+        // two-phase engine: persistent warps, every lane claims blocks; the lanes in use are spread evenly over the warps
+        int64_t ctas = (int64_t) sm_count * kStreamCtasPerSm;
+        const int64_t warps = ctas * kStreamWarps;
+        int lanes = (int) ((b.n + warps - 1) / warps);
+        if (lanes > 32) lanes = 32;
+        if (lanes < 1) lanes = 1;
+        const int64_t need = (b.n + (int64_t) lanes * kStreamWarps - 1) / ((int64_t) lanes * kStreamWarps);
+        if (ctas > need) ctas = need;
         if (ctas < 1) ctas = 1;
-        lz4_stream_decompress_kernel<<<(unsigned) ctas, (kLz4StreamSlots + 1) * 32, smem, st>>>(b);
+        lz4_stream_decompress_kernel<<<(unsigned) ctas, kStreamWarps * 32, 0, st>>>(b, lanes);
         return;
     }
     // version 1: warp-per-block step decoder (round 1): multi-sequence + medium steps, registers bounded for 8 resident

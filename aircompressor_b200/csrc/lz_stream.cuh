@@ -1,412 +1,190 @@
-// lz_stream.cuh -- the streaming LZ77 decode engine shared by the LZ4 and Snappy block decoders (sm_100a).
+// lz_stream.cuh -- the two-phase LZ77 decode engine shared by the LZ4 and Snappy block decoders (sm_100a).
 //
 // A byte-oriented LZ decoder has two very different halves: walking the token grammar is a serial chain of tiny
-// dependent steps (one token decides where the next one starts), while producing the bytes is wide copy work.  This
-// engine gives each half the execution shape it wants:
+// dependent steps (one token decides where the next one starts), while producing the bytes is wide copy work.  A warp
+// that does both for ONE block spends most of its instructions on the serial half with one useful lane.  Here every warp
+// owns up to 32 blocks and alternates between two phases:
 //
-//   * one PARSE warp per CTA walks the grammars of up to kSlots blocks at once, ONE BLOCK PER LANE, so a warp
-//     instruction advances up to 32 independent token chains.  A lane reads its block's compressed bytes from a
-//     2 KiB shared-memory ring that it keeps filled with 512-byte cp.async.bulk copies (mbarrier complete_tx), and
-//     turns sequences / elements into 16-byte RECORDS {literal position, output position, literal length, match
-//     length, offset} in a per-block shared-memory queue;
-//   * one EXECUTE warp per block drains that queue: literals come from the input ring, match bytes from a 4 KiB
-//     shared-memory output ring (only matches farther back than the ring go to L2), a whole short sequence is one
-//     shared-memory load + store per lane, and finished output leaves the ring in 16-byte stores (512 B per warp
-//     instruction pair).
+//   PARSE   every lane walks the grammar of ITS OWN block for up to kRecPerLane sequences: a warp instruction advances up
+//           to 32 independent token chains.  A lane reads its compressed bytes through a private 32-byte shared-memory
+//           window (refilled with two aligned 16-byte loads: one global wavefront per ~4 sequences instead of one per
+//           byte) and writes 8-byte RECORDS {literal length, match length, offset, header bytes skipped} to its row of
+//           the warp's shared-memory record table;
+//   EXECUTE the warp takes the rows one block at a time and produces the bytes: a whole short sequence is ONE load (a
+//           literal of the input or an older output byte, selected per lane) and ONE store per lane; long literal runs and
+//           long / overlapping matches use the 16-byte warp copies of acc_device.cuh.
 //
-// The parse lanes only accept what they can prove the reference decoder would take on its normal path
+// The parse lanes only accept what they can prove the reference decoder takes on its normal path
 // (Lz4RawDecompressor.java:59-195, SnappyRawDecompressor.java:70-220); everything else -- the end-of-block rules,
-// malformed input, very long lengths -- ends the fast path with a FALLBACK record at a token boundary, and the execute
-// warp finishes the block from that (input, output) position with the exact restatement of the Java loop
-// (lz4_decode_v1.cuh general path / snappy_decode_from).  Accept/reject decisions, error offsets and output bytes are
-// therefore those of the general path by construction.
+// malformed input, very long lengths -- ends the fast path at a token boundary, and the warp finishes that block from
+// the (input, output) position of the token with the exact restatement of the Java loop (lz4_decode_v1.cuh general path /
+// snappy_decode_from).  Accept/reject decisions, error offsets and output bytes are therefore those of the general path
+// by construction.
+//
+// (A first version of this engine gave the two halves to different warps -- one parse warp feeding 31 execute warps
+// through shared-memory queues, input staged by cp.async.bulk.  It was bit-exact but 4x slower than round 1: a single
+// warp issues a dependent instruction every ~5 cycles, so one parse warp capped the SM at 0.25 B/cycle however many
+// lanes it used.  profiles/README.md keeps the numbers.)
 //
 // The same source compiles for the host with LZS_EMU defined (tests/host/lzs_emu.cpp: OS threads as lanes), which is
-// how the queue / ring protocol is checked on the CPU before it ever runs on a GPU.
+// how the parse logic and the phase hand-over are checked on the CPU (tests/test_stream_engine_emu.py).
 #pragma once
 #include "acc_device.cuh"
 
 namespace lzs {
 
-constexpr int kInRing = 2048;             // compressed bytes staged per block slot
-constexpr int kChunk = 512;               // one bulk copy
-constexpr int kNChunk = kInRing / kChunk;
-constexpr int kOutRing = 4096;            // decoded bytes kept in shared memory per block slot
-constexpr int kNRec = 64;                 // record queue entries per block slot
-constexpr int kBatch = 16;                // records an execute warp takes before it publishes its progress
-constexpr int kLitPiece = 1024;           // longest literal-only record (long runs are cut into pieces)
-constexpr int kFlushBytes = 512;          // output leaves the ring in pieces of this size (32 lanes x 16 bytes)
-constexpr uint32_t kNoOffset = 0x7fffffffu;
-constexpr uint32_t kSpinLimit = 1u << 24;  // polls without progress before a wait is declared dead (seconds; a launch takes milliseconds)
+constexpr int kRecPerLane = 16;                 // records a lane may produce per parse phase
+constexpr int kRecStride = kRecPerLane + 1;     // row pitch in records (odd: rows start in different banks)
+constexpr int kWinBytes = 32;                   // per-lane input window
+constexpr int kWinStride = 48;                  // window pitch (16-byte aligned, spreads the lanes over the banks)
+constexpr uint32_t kNoOffset = 0xffffffu;       // offset field of a literal-only record
+constexpr int kMaxLitPiece = 4095;              // ll field: 12 bits (longer runs are cut into pieces)
+constexpr uint32_t kMaxMatch = (1u << 20) - 1;  // ml field: 20 bits
+constexpr uint32_t kMaxOffset = (1u << 24) - 2; // off field: 24 bits
+constexpr int kMaxSkip = 255;                   // skip field: 8 bits
+constexpr uint32_t kWholeBlock = 0xffffffffu;   // restart position meaning "the general path decodes the whole block"
 
-// control records have z == 0; w says which
-constexpr uint32_t kRecBegin = 1;         // x = block index
-constexpr uint32_t kRecFallback = 2;      // x = input position, y = output position (block space): finish with the general path
-constexpr uint32_t kRecExit = 3;
-constexpr uint32_t kFallbackWhole = 0xffffffffu;   // x of a FALLBACK record: decode the whole block with the general path (preamble included)
-
-struct __align__(16) Slot {
-    uint8_t in_ring[kInRing];
-    uint8_t out_ring[kOutRing];
-    uint4 rec[kNRec];
-    unsigned long long mbar[kNChunk];
-    uint32_t prod;        // records produced (parse lane)
-    uint32_t cons;        // records consumed (execute warp)
-    uint32_t cons_q;      // running input position below which the execute warp needs nothing any more
-    uint32_t abort;       // watchdog: set when a wait took implausibly long; everybody leaves
+struct __align__(16) WarpSmem {
+    uint8_t win[32 * kWinStride];
+    uint2 rec[32 * kRecStride];
 };
-static_assert(sizeof(Slot) % 16 == 0, "slot alignment");
 
-// ------------------------------------------------------------------------------------------------------------------
-// platform layer: PTX on the device, plain atomics in the host emulation
-// ------------------------------------------------------------------------------------------------------------------
 #ifndef LZS_EMU
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) { uint32_t v; asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
-__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory"); }
-__device__ __forceinline__ void mbar_init(unsigned long long *b) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(b)) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// one bulk copy global -> shared, completion (byte count) signalled on `bar`; src/dst 16-byte aligned, bytes % 16 == 0
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned long long *b, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ uint32_t claim_block(unsigned int *counter) { return atomicAdd(counter, 1u); }
-__device__ __forceinline__ void backoff(unsigned ns) { __nanosleep(ns); }
-__device__ __forceinline__ bool any_lane(bool v) { return __any_sync(__activemask(), v); }   // a scheduling hint only
-__device__ __forceinline__ uint8_t ld_far(const uint8_t *p) { return __ldcg(p); }   // older output of this block: L2 (bypasses L1, always coherent)
-// a shared-memory word read by all lanes of a warp in one instruction: every lane sees the same value
-__device__ __forceinline__ uint32_t warp_ld_acquire(const uint32_t *p, int) { return ld_acquire(p); }
-__device__ __forceinline__ uint32_t warp_ld_relaxed(const uint32_t *p, int) { return ld_relaxed(p); }
 #else
-// host emulation (tests/host/lzs_emu.cpp): threads as lanes, a DMA thread lands the bulk copies late and out of order
-inline void st_release(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-inline uint32_t ld_acquire(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-inline uint32_t ld_relaxed(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
-inline void st_relaxed(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
-inline void mbar_init(unsigned long long *b) { *b = 0; }
-inline void fence_proxy_async() {}
-void emu_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar);
-void emu_count_record(uint32_t z, uint32_t w, uint32_t x, uint32_t y);
-inline void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) { emu_bulk_load(dst, src, bytes, bar); }
-inline bool mbar_test(unsigned long long *b, uint32_t parity) { return ((uint32_t) __atomic_load_n(b, __ATOMIC_ACQUIRE) & 1u) != parity; }
 inline uint32_t claim_block(unsigned int *counter) { return __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED); }
-inline void backoff(unsigned) { sched_yield(); }
-inline bool any_lane(bool v) { return v; }
-inline uint8_t ld_far(const uint8_t *p) { return *(const volatile uint8_t *) p; }
-inline uint32_t warp_bcast(uint32_t v, int lane)
-{
-    if (lane == 0) t_warp->bcast = v;
-    __syncwarp();
-    const uint32_t r = t_warp->bcast;
-    __syncwarp();
-    return r;
-}
-inline uint32_t warp_ld_acquire(const uint32_t *p, int lane) { return warp_bcast(lane == 0 ? ld_acquire(p) : 0, lane); }
-inline uint32_t warp_ld_relaxed(const uint32_t *p, int lane) { return warp_bcast(lane == 0 ? ld_relaxed(p) : 0, lane); }
 #endif
 
-struct BlockDesc {
-    const uint8_t *in;
-    uint8_t *out;
-    int64_t in_len, out_cap;
-};
-__device__ __forceinline__ BlockDesc load_desc(const AccBatch &b, uint32_t idx)
-{
-    BlockDesc d;
-    d.in = b.src + b.src_off[idx];
-    d.in_len = b.src_len[idx];
-    d.out = b.dst + b.dst_off[idx];
-    d.out_cap = b.dst_cap[idx];
-    return d;
-}
+enum ParseResult { kBudgetUsed = 0, kFallback = 2 };
 
-// ------------------------------------------------------------------------------------------------------------------
-// parse side
-// ------------------------------------------------------------------------------------------------------------------
-enum ParseResult { kProgress = 0, kWait = 1, kFallback = 2 };
-
-// what a codec's parse step sees of its lane's block
+// What a codec's parse loop sees of its lane's block.  All positions are relative to `in`.
 struct ParseCtx {
-    Slot *S;
-    uint32_t Qb;          // running ring position of block position 0
-    int32_t in_len;       // block length (after the codec's preamble, if it has one)
-    int32_t out_cap;
-    int32_t avail;        // block positions [0, avail) have landed in the ring
-    uint32_t oh;          // output misalignment: output position p lives at ring / flush position p + oh
-    uint32_t prod;        // records written so far (published by the engine at the end of the round)
+    const uint8_t *in;        // first byte the grammar walk reads (behind the codec's preamble, if it has one)
+    int32_t in_len, out_cap;
+    uint8_t *win;             // this lane's 32-byte window
+    uint2 *rec;               // this lane's record row
+    uint32_t win_tag;         // the aligned 32-byte chunk the window holds; ~0: none
+    uint32_t head;            // (address of in) & 31
+    int32_t prev_lit_end;     // input position behind the literals of the previous record
+    int n_rec;                // records written in this phase
 
-    __device__ __forceinline__ uint32_t byte(int32_t p) const { return S->in_ring[(Qb + (uint32_t) p) & (kInRing - 1)]; }
-    __device__ __forceinline__ void emit(uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+    // one input byte; positions only ever move forward, so a chunk is loaded at most once
+    __device__ __forceinline__ uint32_t byte(int32_t p)
     {
-        S->rec[prod & (kNRec - 1)] = make_uint4(x, y, z, w);
-        prod++;
-#ifdef LZS_EMU
-        emu_count_record(z, w, x, y);
-#endif
+        const uint32_t q = (uint32_t) p + head;
+        if ((q >> 5) != win_tag) {
+            win_tag = q >> 5;
+            const uint4 *src = reinterpret_cast<const uint4 *>(in - head + ((size_t) win_tag << 5));
+            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            *reinterpret_cast<uint4 *>(win) = a;
+            *reinterpret_cast<uint4 *>(win + 16) = b;
+        }
+        return win[q & 31];
     }
-    // a sequence: ll literals at block position lit_pos, then ml bytes copied from `off` back; output starts at op
-    __device__ __forceinline__ void emit_seq(int32_t lit_pos, int32_t op, uint32_t ll, uint32_t ml, uint32_t off)
+    // ll literals at input position lit_pos, then ml bytes copied from `off` back.  false: does not fit a record
+    __device__ __forceinline__ bool emit(int32_t lit_pos, uint32_t ll, uint32_t ml, uint32_t off)
     {
-        emit(Qb + (uint32_t) lit_pos, (uint32_t) op + oh, ll | (ml << 12), off);
+        const int32_t skip = lit_pos - prev_lit_end;
+        if (skip > kMaxSkip || ml > kMaxMatch || (off > kMaxOffset && off != kNoOffset)) return false;
+        rec[n_rec++] = make_uint2(ll | (ml << 12), off | ((uint32_t) skip << 24));
+        prev_lit_end = lit_pos + (int32_t) ll;
+        return true;
     }
 };
 
-// One lane of the parse warp: claims blocks, keeps the input ring filled, runs the codec's parse step.
-template <class Codec>
-__device__ void parse_lane(const AccBatch &b, Slot &S)
+// ------------------------------------------------------------------------------------------------------------------
+// execute: the records of one block (all lanes hold the same arguments)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void execute_records(const uint2 *rec, const int cnt, const uint8_t *in, uint8_t *out, uint32_t lit, uint32_t op, const int lane)
 {
-    enum { kIdle = 0, kRun = 1 };
-    int state = kIdle;
-    uint32_t g_issued = 0, g_ready = 0, g_end = 0, g0 = 0;   // running chunk counters (never reset: they carry the mbarrier phases)
-    const uint8_t *in_al = nullptr;                          // 16-byte aligned start of the first chunk
-    uint32_t stream_q = 0;                                   // head + block length: bytes of aligned stream
-    uint32_t published = 0;
-    uint32_t spins = 0;
+    for (int k = 0; k < cnt; k++) {
+        const uint2 r = rec[k];
+        const uint32_t ll = r.x & 0xfffu, ml = r.x >> 12, off = r.y & 0xffffffu;
+        lit += r.y >> 24;
+        const uint32_t total = ll + ml;
+        if (total <= 32 && off >= total) {
+            // the whole sequence in one step: every lane owns one output byte, a literal of the input or a match byte that
+            // lies completely in front of this sequence (offset >= total)
+            const uint32_t t = (uint32_t) lane;
+            if (t < total) {
+                const uint8_t *p = t < ll ? in + (lit + t) : out + (op + t - off);
+                out[op + t] = *p;
+            }
+        }
+        else {
+            warp_copy(out + op, in + lit, ll, lane);
+            if (ml) {
+                __syncwarp();
+                warp_match_copy(out + (op + ll), off, ml, lane);
+            }
+        }
+        __syncwarp();
+        lit += ll;
+        op += total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// one warp: claims blocks for its lanes, alternates parse and execute phases until the batch is exhausted
+// ------------------------------------------------------------------------------------------------------------------
+template <class Codec>
+__device__ void run_warp(const AccBatch &b, WarpSmem &sm, const int lane, const int lanes_in_use)
+{
     ParseCtx C;
-    C.S = &S; C.prod = 0; C.Qb = 0; C.in_len = 0; C.out_cap = 0; C.avail = 0; C.oh = 0;
+    C.win = sm.win + lane * kWinStride;
+    C.rec = sm.rec + lane * kRecStride;
+    C.in = nullptr; C.in_len = 0; C.out_cap = 0; C.win_tag = ~0u; C.head = 0; C.prev_lit_end = 0; C.n_rec = 0;
     typename Codec::Parse P;
+    Codec::begin(P);
+    uint8_t *out = nullptr;
+    uint32_t blk = 0;
+    bool active = false, exhausted = lane >= lanes_in_use;
     for (;;) {
-        const uint32_t cons = ld_acquire(&S.cons);
-        bool progress = false;
-        // ---- input ring: issue the next chunk when its ring slot is free, note chunks that have landed ----
-        if (g_issued != g_end) {
-            const uint32_t cq = ld_relaxed(&S.cons_q);
-            if ((int32_t) (cq - (g_issued - (kNChunk - 1)) * kChunk) >= 0) {
-                const uint32_t c = g_issued - g0;
-                uint32_t bytes = stream_q - c * kChunk;
-                bytes = bytes >= (uint32_t) kChunk ? (uint32_t) kChunk : ((bytes + 15u) & ~15u);
-                fence_proxy_async();    // the ring slot was last read through the generic proxy
-                bulk_load(S.in_ring + (g_issued & (kNChunk - 1)) * kChunk, in_al + (size_t) c * kChunk, bytes, &S.mbar[g_issued & (kNChunk - 1)]);
-                g_issued++;
-                progress = true;
+        // ---- claim ----
+        if (!active && !exhausted) {
+            const uint32_t idx = claim_block(b.work_counter);
+            if ((int64_t) idx >= b.n) exhausted = true;
+            else {
+                blk = idx;
+                const uint8_t *in = b.src + b.src_off[idx];
+                const int64_t in_len = b.src_len[idx], out_cap = b.dst_cap[idx];
+                out = b.dst + b.dst_off[idx];
+                active = true;
+                C.in = in;
+                C.head = (uint32_t) ((uintptr_t) in & 31);
+                C.win_tag = ~0u;
+                C.prev_lit_end = 0;
+                Codec::begin(P);
+                if (in_len >= 0x7fffff00LL || out_cap >= 0x7fffff00LL || in_len < 32) { C.in_len = 0; C.out_cap = 0; Codec::whole(P); }
+                else { C.in_len = (int32_t) in_len; C.out_cap = (int32_t) out_cap; }
             }
         }
-        if (g_ready != g_issued && mbar_test(&S.mbar[g_ready & (kNChunk - 1)], (g_ready / kNChunk) & 1)) {
-            g_ready++;
-            progress = true;
-        }
-        if (state == kIdle) {
-            // the previous block is finished when the execute warp has taken its FALLBACK record and every bulk copy
-            // issued for it has landed
-            if (cons == C.prod && g_ready == g_issued) {
-                const uint32_t idx = claim_block(b.work_counter);
-                if ((int64_t) idx >= b.n) {
-                    C.emit(0, 0, 0, kRecExit);
-                    st_release(&S.prod, C.prod);
-                    return;
-                }
-                const BlockDesc d = load_desc(b, idx);
-                C.emit(idx, 0, 0, kRecBegin);
-                const bool big = d.in_len >= 0x7fffff00LL || d.out_cap >= 0x7fffff00LL;
-                if (big || d.in_len < 32) {
-                    C.emit(kFallbackWhole, 0, 0, kRecFallback);
-                }
-                else {
-                    const uint32_t head = (uint32_t) ((uintptr_t) d.in & 15);
-                    in_al = d.in - head;
-                    stream_q = head + (uint32_t) d.in_len;
-                    g0 = g_issued;
-                    g_end = g0 + (stream_q + kChunk - 1) / kChunk;
-                    C.Qb = g0 * kChunk + head;
-                    C.in_len = (int32_t) d.in_len;
-                    C.out_cap = (int32_t) d.out_cap;
-                    C.oh = (uint32_t) ((uintptr_t) d.out & 15);
-                    st_relaxed(&S.cons_q, g0 * kChunk);   // the execute warp is idle: nobody else writes this now
-                    Codec::begin(P);
-                    state = kRun;
-                }
-                progress = true;
-            }
-        }
-        else if (C.prod - cons < (uint32_t) kNRec) {
-            const int32_t landed = (int32_t) ((g_ready - g0) * kChunk) - (int32_t) (C.Qb - g0 * kChunk);
-            C.avail = landed < C.in_len ? landed : C.in_len;
-            const int r = Codec::parse_step(P, C);
-            if (r == kFallback) {
-                C.emit(Codec::fallback_ip(P), Codec::fallback_op(P), 0, kRecFallback);
-                g_end = g_issued;       // no further chunks of this block
-                state = kIdle;
-                progress = true;
-            }
-            else if (r == kProgress) progress = true;
-        }
-        if (C.prod != published) {
-            st_release(&S.prod, C.prod);
-            published = C.prod;
-        }
-        if (progress) spins = 0;
-        else if (++spins > kSpinLimit || ld_relaxed(&S.abort)) { st_relaxed(&S.abort, 1); return; }
-        if (!any_lane(progress)) backoff(64);   // nothing to do for any block of this warp: leave the issue slots to the execute warps
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// execute side
-// ------------------------------------------------------------------------------------------------------------------
-// Moves [flushed, e) from the output ring to global memory: 16-byte stores for whole aligned units, bytes for the partial
-// unit at the start of a block and (final flush only) at its end.  Positions are block output position + oh.
-__device__ __forceinline__ void flush_to(const uint8_t *ring, uint8_t *out_al, uint32_t &flushed, const uint32_t e, const int lane)
-{
-    uint32_t a = flushed;
-    if (a & 15u) {
-        uint32_t a1 = (a + 15u) & ~15u;
-        if (a1 > e) a1 = e;
-        if (a + (uint32_t) lane < a1) out_al[a + lane] = ring[(a + lane) & (kOutRing - 1)];
-        a = a1;
-    }
-    const uint32_t units = (e - a) >> 4;
-    for (uint32_t u = (uint32_t) lane; u < units; u += 32) {
-        const uint32_t w = a + (u << 4);
-        *reinterpret_cast<uint4 *>(out_al + w) = *reinterpret_cast<const uint4 *>(ring + (w & (kOutRing - 1)));
-    }
-    a += units << 4;
-    if (a + (uint32_t) lane < e) out_al[a + lane] = ring[(a + lane) & (kOutRing - 1)];
-    flushed = e;
-    __syncwarp();
-}
-
-template <class Codec>
-__device__ void exec_warp(const AccBatch &b, Slot &S, const int lane)
-{
-    uint8_t *const sb = S.in_ring;               // in_ring at [0, kInRing), out_ring behind it
-    uint8_t *const ring = S.out_ring;
-    uint32_t cons = 0;
-    uint32_t blk = 0, flushed = 0;
-    uint8_t *out_al = nullptr;
-    uint32_t spins = 0;
-    for (;;) {
-        const uint32_t prod = warp_ld_acquire(&S.prod, lane);
-        if (prod == cons) {
-            backoff(64);
-            if (++spins > kSpinLimit || warp_ld_relaxed(&S.abort, lane)) {
-                if (lane == 0) { st_relaxed(&S.abort, 1); if (out_al) { b.out_len[blk] = 0; b.status[blk] = ACC_STATUS(ACC_E_CUDA, 0); } }
-                return;
-            }
-            continue;
-        }
-        spins = 0;
-        uint32_t n = prod - cons;
-        if (n > (uint32_t) kBatch) n = kBatch;
-        uint32_t last_q = 0;
-        bool have_q = false;
-        for (uint32_t k = 0; k < n; k++) {
-            const uint4 r = S.rec[(cons + k) & (kNRec - 1)];
-            if (r.z != 0) {
-                const uint32_t ll = r.z & 0xfffu, ml = r.z >> 12, off = r.w, opw = r.y, lq = r.x;
-                const uint32_t total = ll + ml;
-                const uint32_t endw = opw + total;
-                last_q = lq + ll;
-                have_q = true;
-                if (total <= 32 && off >= total) {
-                    // the whole sequence in one step: every lane owns one output byte, a literal from the input ring or a
-                    // match byte that lies completely in front of this sequence (offset >= total)
-                    const uint32_t t = (uint32_t) lane;
-                    if (t < total) {
-                        const uint32_t srcw = opw + t - off;
-                        const bool lit = t < ll;
-                        uint32_t v;
-                        if (lit || (int32_t) (srcw - (endw - kOutRing)) >= 0) v = sb[lit ? ((lq + t) & (kInRing - 1)) : (kInRing + (srcw & (kOutRing - 1)))];
-                        else v = ld_far(out_al + srcw);
-                        ring[(opw + t) & (kOutRing - 1)] = (uint8_t) v;
-                    }
-                    __syncwarp();
-                }
-                else {
-                    for (uint32_t i = (uint32_t) lane; i < ll; i += 32) ring[(opw + i) & (kOutRing - 1)] = sb[(lq + i) & (kInRing - 1)];
-                    __syncwarp();
-                    const uint32_t mopw = opw + ll;
-                    // matches run in pieces of at most kFlushBytes so that the ring can drain in between
-                    for (uint32_t cb = 0; cb < ml; cb += kFlushBytes) {
-                        const uint32_t pw = mopw + cb;                              // first byte of this piece
-                        const uint32_t pn = ml - cb < (uint32_t) kFlushBytes ? ml - cb : (uint32_t) kFlushBytes;
-                        if (off >= 32) {
-                            for (uint32_t base = 0; base < pn; base += 32) {
-                                const uint32_t i = base + (uint32_t) lane;
-                                if (i < pn) {
-                                    const uint32_t pos = pw + i, src = pos - off;
-                                    uint32_t v;
-                                    if ((int32_t) (src - (pw + base + 32 - kOutRing)) >= 0) v = ring[src & (kOutRing - 1)];
-                                    else v = ld_far(out_al + src);
-                                    ring[pos & (kOutRing - 1)] = (uint8_t) v;
-                                }
-                                __syncwarp();
-                            }
-                        }
-                        else {
-                            // periodic pattern: every byte of the piece repeats one of the `off` bytes in front of it
-                            uint32_t m = (uint32_t) lane % off;
-                            const uint32_t step = 32u % off;
-                            for (uint32_t i = (uint32_t) lane; i < pn; i += 32) {
-                                ring[(pw + i) & (kOutRing - 1)] = ring[(pw - off + m) & (kOutRing - 1)];
-                                m += step;
-                                if (m >= off) m -= off;
-                            }
-                            __syncwarp();
-                        }
-                        if (pw + pn - flushed >= (uint32_t) kFlushBytes) flush_to(ring, out_al, flushed, (pw + pn) & ~15u, lane);
-                    }
-                }
-                if (endw - flushed >= (uint32_t) kFlushBytes) flush_to(ring, out_al, flushed, endw & ~15u, lane);
-            }
-            else if (r.w == kRecBegin) {
-                blk = r.x;
-                uint8_t *out = b.dst + b.dst_off[blk];
-                const uint32_t oh = (uint32_t) ((uintptr_t) out & 15);
-                out_al = out - oh;
-                flushed = oh;
-            }
-            else if (r.w == kRecFallback) {
-                const BlockDesc d = load_desc(b, blk);
-                if (r.x == kFallbackWhole) Codec::general_whole(d, b, blk, lane);
-                else {
-                    // everything in front of the restart point must be in global memory (literal pieces of the sequence
-                    // the general path decodes again may already be there: it rewrites the same bytes)
-                    const uint32_t e = r.y + (uint32_t) ((uintptr_t) d.out & 15);
-                    if ((int32_t) (e - flushed) > 0) flush_to(ring, out_al, flushed, e, lane);
-                    Codec::general_from(d, b, blk, r.x, r.y, lane);
-                }
+        if (!__any_sync(kFull, active)) break;
+        // ---- parse phase ----
+        const uint32_t x_lit = (uint32_t) C.prev_lit_end, x_op = Codec::out_pos(P);
+        C.n_rec = 0;
+        bool fb = false;
+        if (active) fb = Codec::is_whole(P) || Codec::parse_run(P, C, kRecPerLane) == kFallback;
+        __syncwarp();
+        // ---- execute phase ----
+        unsigned todo = __ballot_sync(kFull, active && (C.n_rec > 0 || fb));
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int cnt = __shfl_sync(kFull, C.n_rec, src);
+            const uint8_t *in_b = (const uint8_t *) __shfl_sync(kFull, (unsigned long long) C.in, src);
+            uint8_t *out_b = (uint8_t *) __shfl_sync(kFull, (unsigned long long) out, src);
+            const uint32_t lit_b = __shfl_sync(kFull, x_lit, src), op_b = __shfl_sync(kFull, x_op, src);
+            if (cnt) execute_records(sm.rec + src * kRecStride, cnt, in_b, out_b, lit_b, op_b, lane);
+            if (__shfl_sync(kFull, (int) fb, src)) {
+                const uint32_t blk_b = __shfl_sync(kFull, blk, src);
+                const uint32_t fip = __shfl_sync(kFull, Codec::fallback_ip(P), src), fop = __shfl_sync(kFull, Codec::fallback_op(P), src);
+                Codec::finish(b, blk_b, fip, fop, lane);
                 __syncwarp();
             }
-            else {   // kRecExit
-                return;
-            }
         }
-        cons += n;
-        __syncwarp();
-        if (lane == 0) {
-            if (have_q) st_relaxed(&S.cons_q, last_q);
-            st_release(&S.cons, cons);
-        }
+        if (fb) active = false;
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// kernel body: warps [0, kSlots) execute, warp kSlots parses (one lane per slot)
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void init_slot(Slot &S)
-{
-    S.prod = 0; S.cons = 0; S.cons_q = 0; S.abort = 0;
-    for (int i = 0; i < kNChunk; i++) mbar_init(&S.mbar[i]);
-}
-
-template <class Codec, int kSlots>
-__device__ __forceinline__ void run_warp(const AccBatch &b, Slot *slots, const int warp, const int lane)
-{
-    if (warp == kSlots) {
-        if (lane < kSlots) parse_lane<Codec>(b, slots[lane]);
-    }
-    else exec_warp<Codec>(b, slots[warp], lane);
 }
 
 }  // namespace lzs

@@ -26,16 +26,13 @@ __global__ void __launch_bounds__(256, kMinCtas) snappy_decompress_kernel(AccBat
     }
 }
 
-constexpr int kSnStreamSlots = 31;
+constexpr int kStreamWarps = 8;        // warps per CTA of the two-phase decoder
+constexpr int kStreamCtasPerSm = 4;    // 32 warps per SM, each owning up to 32 blocks
 
-__global__ void __launch_bounds__((kSnStreamSlots + 1) * 32, 1) snappy_stream_decompress_kernel(AccBatch b)
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) snappy_stream_decompress_kernel(AccBatch b, int lanes_in_use)
 {
-    extern __shared__ __align__(128) uint8_t lzs_smem[];
-    lzs::Slot *slots = reinterpret_cast<lzs::Slot *>(lzs_smem);
-    if (threadIdx.x < kSnStreamSlots) lzs::init_slot(slots[threadIdx.x]);
-    lzs::fence_proxy_async();
-    __syncthreads();
-    lzs::run_warp<SnappyStream, kSnStreamSlots>(b, slots, threadIdx.x >> 5, lane_id());
+    __shared__ lzs::WarpSmem sm[kStreamWarps];
+    lzs::run_warp<SnappyStream>(b, sm[threadIdx.x >> 5], lane_id(), lanes_in_use);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -190,13 +187,16 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
 void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
     if (version == 0 || version == 2) {
-        // streaming engine: one CTA per SM, 31 blocks in flight per CTA
-        const int smem = kSnStreamSlots * (int) sizeof(lzs::Slot);
-        cudaFuncSetAttribute(snappy_stream_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        int64_t ctas = (b.n + kSnStreamSlots - 1) / kSnStreamSlots;
-        if (ctas > sm_count) ctas = sm_count;
+        // two-phase engine: persistent warps, every lane claims blocks; the lanes in use are spread evenly over the warps
+        int64_t ctas = (int64_t) sm_count * kStreamCtasPerSm;
+        const int64_t warps = ctas * kStreamWarps;
+        int lanes = (int) ((b.n + warps - 1) / warps);
+        if (lanes > 32) lanes = 32;
+        if (lanes < 1) lanes = 1;
+        const int64_t need = (b.n + (int64_t) lanes * kStreamWarps - 1) / ((int64_t) lanes * kStreamWarps);
+        if (ctas > need) ctas = need;
         if (ctas < 1) ctas = 1;
-        snappy_stream_decompress_kernel<<<(unsigned) ctas, (kSnStreamSlots + 1) * 32, smem, st>>>(b);
+        snappy_stream_decompress_kernel<<<(unsigned) ctas, kStreamWarps * 32, 0, st>>>(b, lanes);
         return;
     }
     // version 1: warp-per-block step decoder (round 1)

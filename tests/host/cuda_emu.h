@@ -24,9 +24,12 @@ struct __attribute__((aligned(16))) uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 typedef void *cudaStream_t;
 
+struct __attribute__((aligned(8))) uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
+
 struct EmuWarp {
     pthread_barrier_t bar;
-    volatile uint32_t bcast;
+    volatile unsigned long long xchg[32];
 };
 extern thread_local EmuWarp *t_warp;
 extern thread_local int t_lane;
@@ -34,11 +37,30 @@ extern thread_local int t_lane;
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&t_warp->bar); }
 static inline int lane_id_emu() { return t_lane; }
 
-// warp shuffles / votes are only reached by the round-1 step decoders, which the emulation never selects
+// warp collectives over all 32 lanes (the engine only uses full masks): exchange through the warp's array
+static inline unsigned long long emu_xchg(unsigned long long v, int src)
+{
+    t_warp->xchg[t_lane] = v;
+    __syncwarp();
+    const unsigned long long r = t_warp->xchg[src & 31];
+    __syncwarp();
+    return r;
+}
+static inline unsigned long long __shfl_sync(unsigned, unsigned long long v, int src) { return emu_xchg(v, src); }
+static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return (uint32_t) emu_xchg(v, src); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int) emu_xchg((unsigned long long) (long long) v, src); }
+static inline unsigned __ballot_sync(unsigned, bool p)
+{
+    t_warp->xchg[t_lane] = p ? 1 : 0;
+    __syncwarp();
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned) (t_warp->xchg[i] & 1) << i;
+    __syncwarp();
+    return m;
+}
+static inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 [[noreturn]] static inline void emu_unsupported(const char *what) { fprintf(stderr, "cuda_emu: %s reached\n", what); abort(); }
-static inline uint32_t __shfl_sync(unsigned, uint32_t, int) { emu_unsupported("__shfl_sync"); }
-static inline bool __any_sync(unsigned, bool) { emu_unsupported("__any_sync"); }
-static inline unsigned __ballot_sync(unsigned, bool) { emu_unsupported("__ballot_sync"); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *) p; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh & 31)); }

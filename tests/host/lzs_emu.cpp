@@ -1,6 +1,5 @@
-// lzs_emu.cpp -- runs the streaming LZ77 decode engine (aircompressor_b200/csrc/lz_stream.cuh with the LZ4 and Snappy parse
-// sides) on the CPU: OS threads play the lanes, a DMA thread lands the "bulk copies" late and out of order after
-// poisoning their destination.  The decoded blocks, lengths and status words are written to a file that
+// lzs_emu.cpp -- runs the two-phase LZ77 decode engine (aircompressor_b200/csrc/lz_stream.cuh with the LZ4 and Snappy parse
+// sides) on the CPU: OS threads play the lanes.  The decoded blocks, lengths and status words are written to a file that
 // tests/test_stream_engine_emu.py compares with the oracle.  TEST INFRASTRUCTURE: nothing here ships.
 //
 //   lzs_emu <in-file> <out-file>
@@ -10,8 +9,6 @@
 #define LZS_EMU 1
 #include "cuda_emu.h"
 
-#include <mutex>
-#include <random>
 #include <thread>
 #include <vector>
 
@@ -21,85 +18,23 @@ thread_local int t_lane = 0;
 #include "../../aircompressor_b200/csrc/lz4_stream.cuh"
 #include "../../aircompressor_b200/csrc/snappy_decode.cuh"
 
-// ---- the DMA thread ------------------------------------------------------------------------------------------------
-namespace {
-struct Copy { void *dst; const void *src; uint32_t bytes; unsigned long long *bar; };
-std::mutex g_mu;
-std::vector<Copy> g_pending;
-std::atomic<bool> g_stop{false};
-std::atomic<long> g_copies{0};
-
-void dma_main()
-{
-    std::mt19937 rng(12345);
-    for (;;) {
-        Copy c;
-        bool have = false;
-        {
-            std::lock_guard<std::mutex> lk(g_mu);
-            if (!g_pending.empty()) {
-                const size_t i = rng() % g_pending.size();     // any order
-                c = g_pending[i];
-                g_pending[i] = g_pending.back();
-                g_pending.pop_back();
-                have = true;
-            }
-        }
-        if (!have) {
-            if (g_stop.load()) return;
-            sched_yield();
-            continue;
-        }
-        for (unsigned k = rng() % 200; k; k--) sched_yield();  // late
-        memcpy(c.dst, c.src, c.bytes);
-        __atomic_fetch_add(c.bar, 1ull, __ATOMIC_RELEASE);
-        g_copies++;
-    }
-}
-}  // namespace
-
-namespace lzs {
-void emu_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-    if (((uintptr_t) dst & 15) || ((uintptr_t) src & 15) || (bytes & 15) || bytes == 0 || bytes > (uint32_t) kChunk) {
-        fprintf(stderr, "emu_bulk_load: bad alignment / size (%p %p %u)\n", dst, src, bytes);
-        abort();
-    }
-    memset(dst, 0xEE, bytes);     // the destination is undefined until the copy has landed
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_pending.push_back({dst, src, bytes, bar});
-}
-}  // namespace lzs
-
-std::atomic<long> g_seq_records{0}, g_seq_bytes{0}, g_fallbacks{0}, g_fallback_out{0};
-namespace lzs {
-void emu_count_record(uint32_t z, uint32_t w, uint32_t x, uint32_t y)
-{
-    if (z) { g_seq_records++; g_seq_bytes += (z & 0xfff) + (z >> 12); }
-    else if (w == kRecFallback) { g_fallbacks++; if (x != kFallbackWhole) g_fallback_out += y; }
-}
-}  // namespace lzs
-
-constexpr int kSlots = 3;
+constexpr int kWarps = 3;
 
 template <class Codec>
-static void run(const AccBatch &b)
+static void run(const AccBatch &b, int lanes_in_use)
 {
-    static lzs::Slot slots[kSlots];
-    for (int i = 0; i < kSlots; i++) lzs::init_slot(slots[i]);
-    EmuWarp warps[kSlots + 1];
+    static lzs::WarpSmem sm[kWarps];
+    EmuWarp warps[kWarps];
     for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
     std::vector<std::thread> th;
-    for (int w = 0; w <= kSlots; w++)
+    for (int w = 0; w < kWarps; w++)
         for (int l = 0; l < 32; l++)
             th.emplace_back([&, w, l] {
                 t_warp = &warps[w];
                 t_lane = l;
-                lzs::run_warp<Codec, kSlots>(b, slots, w, l);
+                lzs::run_warp<Codec>(b, sm[w], l, lanes_in_use);
             });
     for (auto &t : th) t.join();
-    for (int i = 0; i < kSlots; i++)
-        if (slots[i].abort) { fprintf(stderr, "slot %d aborted (watchdog)\n", i); exit(3); }
 }
 
 int main(int argc, char **argv)
@@ -138,10 +73,12 @@ int main(int argc, char **argv)
     b.dst = dst; b.dst_off = dst_off.data(); b.dst_cap = dst_cap.data();
     b.out_len = out_len.data(); b.status = status.data(); b.n = n; b.work_counter = &counter;
 
-    std::thread dma(dma_main);
-    if (codec == 0) run<lz4v1::Lz4Stream>(b); else run<snappydec::SnappyStream>(b);
-    g_stop = true;
-    dma.join();
+    // lanes in use per warp as the launcher computes them (every lane claims blocks until the batch is exhausted)
+    int lanes = (n + kWarps - 1) / kWarps;
+    if (lanes > 32) lanes = 32;
+    if (lanes < 1) lanes = 1;
+    if (getenv("LZS_EMU_LANES")) lanes = atoi(getenv("LZS_EMU_LANES"));
+    if (codec == 0) run<lz4v1::Lz4Stream>(b, lanes); else run<snappydec::SnappyStream>(b, lanes);
 
     FILE *o = fopen(argv[2], "wb");
     if (!o) return 2;
@@ -151,7 +88,6 @@ int main(int argc, char **argv)
         fwrite(dst + dst_off[i], 1, dst_cap[i] + 64, o);
     }
     fclose(o);
-    fprintf(stderr, "lzs_emu: %d blocks, %ld bulk copies, %ld sequence records (%ld bytes), %ld hand-overs to the general path (after %ld bytes)\n", n, g_copies.load(),
-            g_seq_records.load(), g_seq_bytes.load(), g_fallbacks.load(), g_fallback_out.load());
+    fprintf(stderr, "lzs_emu: %d blocks, %d lanes per warp in use\n", n, lanes);
     return 0;
 }

@@ -1,11 +1,10 @@
-"""CPU test of the streaming LZ77 decode engine (aircompressor_b200/csrc/lz_stream.cuh + the LZ4 / Snappy parse sides).
+"""CPU test of the two-phase LZ77 decode engine (aircompressor_b200/csrc/lz_stream.cuh + the LZ4 / Snappy parse sides).
 
-tests/host/lzs_emu.cpp compiles the SAME device source for the host (OS threads as lanes, a DMA thread that lands the
-bulk copies late and out of order after poisoning their destination) and decodes a file of blocks; this test compares
-bytes, lengths, status words and error offsets with the oracle (= Java decoder rules) for valid streams of both
-compressors, corrupted streams, the reference's malformed vectors and every (input, output) misalignment class.  The
-GPU parity tests remain the gate for the kernels themselves; this one checks the queue / ring protocol and the parse
-logic, which a GPU can only report as "hang" or "wrong bytes".
+tests/host/lzs_emu.cpp compiles the SAME device source for the host (OS threads as lanes, barriers as __syncwarp, an
+exchange array as shuffles and ballots) and decodes a file of blocks; this test compares bytes, lengths, status words and
+error offsets with the oracle (= Java decoder rules) for valid streams of both compressors, corrupted streams, the
+reference's malformed vectors and every (input, output) misalignment class.  The GPU parity tests remain the gate for
+the kernels themselves; this one checks the parse logic and the parse -> execute hand-over on the CPU.
 """
 import os
 import struct
