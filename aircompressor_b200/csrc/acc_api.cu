@@ -27,7 +27,7 @@ struct acc_ctx {
     int64_t last_offset = 0;
     int64_t launches = 0;
     int tuning_ctas_per_sm = 0;
-    int tuning_decoder = 0;   // LZ4/Snappy decode kernel: 0 = default, 1 = warp-per-block step decoder, 2 = streaming engine (lz_stream.cuh)
+    int tuning_decoder = 0;   // reserved (one LZ4 / Snappy decode kernel ships)
     int tuning_pipeline = 0;  // host-pointer batches: 0 = auto, 1 = never split, k > 1 = split into k chunks
     // copy streams + events of the pipelined host-pointer path (created on first use)
     static constexpr int kMaxChunks = 16;

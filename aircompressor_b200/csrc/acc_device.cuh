@@ -6,11 +6,7 @@
 // of work is one Compressor/Decompressor call (Compressor.java:18-36, Decompressor.java:18-31).
 #pragma once
 #include <cstdint>
-#ifdef LZS_EMU
-#include "cuda_emu.h"   // host emulation of the streaming decode engine (tests/host)
-#else
 #include <cuda_runtime.h>
-#endif
 #include "../../include/aircompress_cuda.h"
 
 struct AccBatch {
@@ -31,11 +27,7 @@ struct AccBatch {
 static constexpr int kWarp = 32;
 static constexpr unsigned kFull = 0xffffffffu;
 
-#ifdef LZS_EMU
-__device__ __forceinline__ int lane_id() { return lane_id_emu(); }
-#else
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-#endif
 
 __device__ __forceinline__ uint32_t ld_u16le(const uint8_t *p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8); }
 

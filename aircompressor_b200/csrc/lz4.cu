@@ -7,8 +7,6 @@
 // AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
 #include "lz4_decode_v1.cuh"
-#include "lz_stream.cuh"
-#include "lz4_stream.cuh"
 
 namespace {
 
@@ -29,14 +27,6 @@ __global__ void __launch_bounds__(256, kMinCtas) lz4_decompress_kernel(AccBatch 
     }
 }
 
-constexpr int kStreamWarps = 8;        // warps per CTA of the two-phase decoder
-constexpr int kStreamCtasPerSm = 4;    // 32 warps per SM, each owning up to 32 blocks
-
-__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) lz4_stream_decompress_kernel(AccBatch b, int lanes_in_use)
-{
-    __shared__ lzs::WarpSmem sm[kStreamWarps];
-    lzs::run_warp<Lz4Stream>(b, sm[threadIdx.x >> 5], lane_id(), lanes_in_use);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Encode: one warp per block, 4096-entry position table in shared memory (same size as the
@@ -199,21 +189,8 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
 
 void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
-    if (version == 0 || version == 2) {
-        // two-phase engine: persistent warps, every lane claims blocks; the lanes in use are spread evenly over the warps
-        int64_t ctas = (int64_t) sm_count * kStreamCtasPerSm;
-        const int64_t warps = ctas * kStreamWarps;
-        int lanes = (int) ((b.n + warps - 1) / warps);
-        if (lanes > 32) lanes = 32;
-        if (lanes < 1) lanes = 1;
-        const int64_t need = (b.n + (int64_t) lanes * kStreamWarps - 1) / ((int64_t) lanes * kStreamWarps);
-        if (ctas > need) ctas = need;
-        if (ctas < 1) ctas = 1;
-        lz4_stream_decompress_kernel<<<(unsigned) ctas, kStreamWarps * 32, 0, st>>>(b, lanes);
-        return;
-    }
-    // version 1: warp-per-block step decoder (round 1): multi-sequence + medium steps, registers bounded for 8 resident
-    // CTAs (32 registers, 64 warps per SM)
+    // warp-per-block step decoder: multi-sequence + medium steps, registers bounded for 8 resident CTAs (32 registers,
+    // 64 warps per SM)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;

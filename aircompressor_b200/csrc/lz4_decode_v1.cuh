@@ -4,7 +4,7 @@
 //   1. multi-sequence steps: up to three sequences without length-extension bytes per 32-byte window (kFast >= 2)
 //   2. medium steps: one sequence with a single extension byte per length (kFast == 3)
 //   3. the general path: a restatement of the Java loop, sequence by sequence, with warp-wide copies
-// Used by lz4_decompress_kernel (lz4.cu); the general path also finishes the blocks of the streaming engine (lz_stream.cuh).
+// Used by lz4_decompress_kernel (lz4.cu).
 #pragma once
 #include "acc_device.cuh"
 
@@ -26,7 +26,7 @@ __device__ __forceinline__ void lz4_decode_impl(const uint8_t *__restrict__ in_a
 #define LZ4_FAIL(off, reason) do { if (lane == 0) { out_len_base[idx] = (int64_t) (off); status_base[idx] = ACC_STATUS(ACC_E_MALFORMED, reason); } return; } while (0)
     constexpr bool small = sizeof(PosT) == 4;
     const PosT fast_output_limit = out_cap - 8;
-    PosT ip = ip0, op = op0;   // (ip0, op0) != (0, 0): resume at a sequence boundary (lz_stream.cuh hands blocks over this way)
+    PosT ip = ip0, op = op0;   // (ip0, op0) != (0, 0): resume at a sequence boundary
     // base pointers made opaque, so that the compiler keeps these two 64-bit values in registers instead of re-adding
     // kernel parameters (and holding the parts) inside the loops
     const uint8_t *in = in_arg;

@@ -5,7 +5,6 @@
 // the Java decoder (same accept/reject decisions and error offsets); encode emits a valid stream the
 // Java decoder round-trips (AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
-#include "lz_stream.cuh"
 #include "snappy_decode.cuh"
 
 namespace {
@@ -26,14 +25,6 @@ __global__ void __launch_bounds__(256, kMinCtas) snappy_decompress_kernel(AccBat
     }
 }
 
-constexpr int kStreamWarps = 8;        // warps per CTA of the two-phase decoder
-constexpr int kStreamCtasPerSm = 4;    // 32 warps per SM, each owning up to 32 blocks
-
-__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) snappy_stream_decompress_kernel(AccBatch b, int lanes_in_use)
-{
-    __shared__ lzs::WarpSmem sm[kStreamWarps];
-    lzs::run_warp<SnappyStream>(b, sm[threadIdx.x >> 5], lane_id(), lanes_in_use);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Encode: one warp per input; independent 64 KiB fragments (SnappyRawCompressor.java:37-38,93) are
@@ -186,20 +177,6 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
 
 void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
 {
-    if (version == 0 || version == 2) {
-        // two-phase engine: persistent warps, every lane claims blocks; the lanes in use are spread evenly over the warps
-        int64_t ctas = (int64_t) sm_count * kStreamCtasPerSm;
-        const int64_t warps = ctas * kStreamWarps;
-        int lanes = (int) ((b.n + warps - 1) / warps);
-        if (lanes > 32) lanes = 32;
-        if (lanes < 1) lanes = 1;
-        const int64_t need = (b.n + (int64_t) lanes * kStreamWarps - 1) / ((int64_t) lanes * kStreamWarps);
-        if (ctas > need) ctas = need;
-        if (ctas < 1) ctas = 1;
-        snappy_stream_decompress_kernel<<<(unsigned) ctas, kStreamWarps * 32, 0, st>>>(b, lanes);
-        return;
-    }
-    // version 1: warp-per-block step decoder (round 1)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;

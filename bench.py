@@ -266,7 +266,6 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short per-codec side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--decoder", type=int, default=0, help="LZ4/Snappy decode kernel: 1 warp-per-block step decoder, 2 streaming engine, 0 library default")
     ap.add_argument("--pipeline", type=int, default=0, help="host-pointer path: 0 auto, 1 single pass, k>1 overlapped runs")
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): no e2e, no cpu baseline, warm-up as given")
     args = ap.parse_args()
@@ -304,8 +303,6 @@ def main():
     eng = acb.BatchEngine(local_rank)
     if args.ctas_per_sm:
         eng.set_tuning(0, args.ctas_per_sm)
-    if args.decoder:
-        eng.set_tuning(1, args.decoder)
     op = CODEC_OPS[(args.codec, args.op)]
     n = args.blocks
 
