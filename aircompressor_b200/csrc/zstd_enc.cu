@@ -8,17 +8,28 @@
 // (oracle) and by libzstd and reproduce the input (AbstractTestCompression.java:362-393); compressed bytes
 // are not expected to be identical to the Java compressor's.
 //
-// Mapping: one 128-thread CTA per input.  Per block (<= 128 KiB):
-//   1. match finding: the 4 warps parse one quarter of the block each, sharing a 8192-entry position table
-//      in shared memory; 32 positions are probed per step, ballot picks the first 4-byte match, a second
-//      ballot extends it.  Sequences are (literal length, match length, offset) triples, so the four
-//      lists concatenate by adding a quarter's trailing literals to the next quarter's first sequence;
-//   2. prefix sums over the sequences give literal-buffer offsets; literals are gathered and histogrammed;
-//   3. Huffman: code lengths (depth limit 11) by one thread, then every symbol's code is OR-ed into the
+// Mapping: one 256-thread CTA per input.  Per block (<= 128 KiB):
+//   1. match finding, the double-fast idea (DoubleFastBlockCompressor.java:28-180: a short and a long hash table, the
+//      repeated offsets tried first) laid out for 8 warps that parse one eighth of the block each:
+//        pass A: every warp fills a "long" table (6-byte hash, 2048 entries) with the LAST position of every value in
+//                its own sub-range -- read-only afterwards, so what a later sub-range finds in it is deterministic;
+//        pass B: every warp probes 32 positions per step: the two most recent offsets of its own parse (repeat
+//                candidates), its incremental "short" table (4-byte hash, 1024 entries: the nearest earlier position
+//                of its own sub-range), then the long tables of the three sub-ranges in front of it (matches across
+//                sub-ranges, up to 64 KiB back; 2 tag bits per entry filter most false candidates before the 6-byte
+//                check).  A ballot picks the first hit, a second ballot extends it.
+//      Sequences are (literal length, match length, offset) triples, so the eight lists concatenate by adding a
+//      sub-range's trailing literals to the next one's first sequence;
+//   2. repeated offsets (RepeatedOffsets.java:16-49, RFC 8878 3.1.1.5): one pass over the concatenated list turns
+//      offsets that equal one of the three most recent ones into repeat codes 1..3 (exact decoder history);
+//   3. prefix sums over the sequences give literal-buffer offsets; literals are gathered and histogrammed;
+//   4. Huffman: code lengths (depth limit 11) by one thread, then every symbol's code is OR-ed into the
 //      output at its bit offset (reverse prefix sum of code lengths), 4 streams on 4 warps;
-//   4. sequences: predefined FSE tables (RFC 8878 3.1.1.3.2.2 / SequenceEncoder.java:36-56); three threads
-//      walk the three state chains, then all threads OR their sequences' bits at prefix-sum offsets;
-//   5. block assembly, raw-block fallback when the gain is below the reference's threshold.
+//   5. sequences (SequenceEncoder.compressSequences :66-209): code histograms, selectEncodingType (:299-341) per
+//      stream -- RLE, predefined, or FSE-compressed with normalizeCounts / writeNormalizedCounts
+//      (FiniteStateEntropy.java:257-521) -- three threads build the tables and walk the three state chains, then all
+//      threads OR their sequences' bits at prefix-sum offsets;
+//   6. block assembly, raw-block fallback when the gain is below the reference's threshold.
 #include "zstd_common.cuh"
 #include "zstd_fse_enc.cuh"
 #include "xxh64_device.cuh"
@@ -28,38 +39,44 @@ using namespace zs;
 
 constexpr int kThreads = 256;
 constexpr int kNQ = kThreads / 32;                         // sub-ranges of a block, one per warp
-constexpr int kHashLog = 13;
+constexpr int kShortLog = 10;                              // incremental table of a sub-range: 4-byte hash
+constexpr int kLongLog = 11;                               // final table of a sub-range: 6-byte hash, 14-bit position + 2 tag bits
+constexpr int kPrevTables = 3;                             // long tables of this many earlier sub-ranges are probed
+constexpr uint16_t kEmpty16 = 0xFFFF;
 constexpr int kMaxSeqQ = kMaxBlock / kNQ / 4 + 16;       // sequences per sub-range (min match 4)
 constexpr int kMaxSeq = kNQ * kMaxSeqQ;
 constexpr int kStreamStage = 48 * 1024;                  // staging bytes per Huffman stream (32768 symbols x 11 bits)
 constexpr int kSeqStage = kMaxBlock + 1024;              // staging bytes for the sequence bitstream
 constexpr int64_t kScratchPerCta = (int64_t) kMaxSeq * 8 + (kMaxBlock + 64) + (int64_t) 3 * kMaxSeq * 2 + 4 * kStreamStage + kSeqStage + 256;
 
-// Slot of a 4-byte value in the position table.  Every warp owns one eighth of the table (its sub-range of the block only
-// ever sees its own insertions), which makes the encoder deterministic: with one shared table the candidate a warp read
-// depended on how far the other warps had come.
-__device__ __forceinline__ uint32_t zenc_slot(uint32_t v, int warp)
-{
-    return ((v * 2654435761u) >> (32 - (kHashLog - 3))) | ((uint32_t) warp << (kHashLog - 3));
-}
+__device__ __forceinline__ uint32_t zenc_short_slot(uint32_t v) { return (v * 2654435761u) >> (32 - kShortLog); }
+// 6-byte hash (hash6 of DoubleFastBlockCompressor.java:216-256): slot in the low kLongLog bits, 2 tag bits above them
+__device__ __forceinline__ uint32_t zenc_long_hash(uint64_t v) { return (uint32_t) (((v << 16) * 0xCF1BBCDCBF9BULL) >> (64 - kLongLog - 2)); }
 
 struct NodeTable { int32_t count[512]; int16_t parents[512]; int16_t symbols[512]; uint8_t nbits[512]; };
 
 struct EncSmem {
-    union { uint32_t hash[1 << kHashLog]; NodeTable nt; } u;
+    union {
+        struct { uint16_t inc[kNQ][1 << kShortLog]; uint16_t fin[kNQ][1 << kLongLog]; } t;   // match finding
+        uint32_t rep[(kNQ << kShortLog) / 2 + (kNQ << kLongLog) / 2];                           // repeat-offset pass: one word per sequence
+        NodeTable nt;                                                                            // Huffman tree
+    } u;
     uint32_t hist[256];
     uint16_t hcode[256];
     uint8_t hbits[256];
-    uint16_t ll_next[64], ml_next[64], of_next[32];
-    int32_t ll_dnb[36], ll_dfs[36], ml_dnb[53], ml_dfs[53], of_dnb[29], of_dfs[29];
+    uint16_t ll_next[512], ml_next[512], of_next[256];     // FSE encode tables of the current block (tableLog <= 9 / 9 / 8)
+    int32_t ll_dnb[36], ll_dfs[36], ml_dnb[53], ml_dfs[53], of_dnb[32], of_dfs[32];
+    int32_t chist[3][56];                                  // code histograms: OF, ML, LL
+    uint8_t tdesc[3][136];                                 // table descriptions (RLE symbol or normalized counts): OF, ML, LL
     int32_t scan[kThreads + 1];
     int32_t qcount[kNQ], qtrail[kNQ], qbase[kNQ + 1];
-    int32_t v[24];   // broadcast slots
+    int32_t v[32];   // broadcast slots
     uint8_t wbuf[264];   // serialized Huffman table description (header byte + weights)
 };
 
 enum { V_NSEQ = 0, V_LASTLIT, V_NLIT, V_LITMODE, V_MAXSYM, V_HUFBITS, V_HTABLE_BYTES, V_STREAM_BYTES0, V_STREAM_BYTES1, V_STREAM_BYTES2,
-       V_STREAM_BYTES3, V_SEQ_TOTAL_BITS, V_FINAL_OF, V_FINAL_ML, V_FINAL_LL, V_LIT_SECTION, V_SEQ_SECTION, V_CHECKSUM };
+       V_STREAM_BYTES3, V_SEQ_TOTAL_BITS, V_FINAL_OF, V_FINAL_ML, V_FINAL_LL, V_LOG_OF, V_LOG_ML, V_LOG_LL, V_MODE_OF, V_MODE_ML, V_MODE_LL,
+       V_DESC_OF, V_DESC_ML, V_DESC_LL, V_CHECKSUM, V_REP1, V_REP2, V_REP3, V_REPT1, V_REPT2, V_REPT3 };
 
 __device__ __forceinline__ uint64_t pack_seq(uint32_t ll, uint32_t ml, uint32_t off) { return (uint64_t) ll | ((uint64_t) ml << 20) | ((uint64_t) off << 40); }
 __device__ __forceinline__ uint32_t seq_ll(uint64_t s) { return (uint32_t) (s & 0xFFFFF); }
@@ -241,6 +258,62 @@ __device__ int huf_build(EncSmem &sm, int max_symbol, int max_bits)
     return largest_bits;
 }
 
+// SequenceEncoder.selectEncodingType (zstd/SequenceEncoder.java:299-341) for strategy DFAST (ordinal 1): 0 basic (predefined
+// table), 1 RLE, 2 FSE-compressed.
+__device__ __forceinline__ int select_seq_encoding(int largest, int nseq, int default_log, bool default_allowed)
+{
+    if (largest == nseq) return (default_allowed && nseq <= 2) ? 0 : 1;
+    if (default_allowed) {
+        const int min_sequences = ((1 << default_log) * 9) >> 3;
+        if (nseq < min_sequences || largest < (nseq >> (default_log - 1))) return 0;
+    }
+    return 2;
+}
+
+// One sequence stream (k: 0 offsets, 1 match lengths, 2 literal lengths) of SequenceEncoder.compressSequences (:96-199):
+// picks the encoding from the code histogram, builds the FSE encode table into shared memory and serialises its
+// description (nothing for the predefined table, the symbol for RLE, writeNormalizedCounts for a compressed table).
+// Single thread.  last_code = code of the last sequence (buildCompressionTable :211-226 leaves it out of the statistics).
+__device__ void build_seq_table(EncSmem &sm, int k, int nseq, int last_code)
+{
+    uint16_t *nx = k == 0 ? sm.of_next : k == 1 ? sm.ml_next : sm.ll_next;
+    int32_t *dnb = k == 0 ? sm.of_dnb : k == 1 ? sm.ml_dnb : sm.ll_dnb;
+    int32_t *dfs = k == 0 ? sm.of_dfs : k == 1 ? sm.ml_dfs : sm.ll_dfs;
+    int32_t *counts = sm.chist[k];
+    const int16_t *def_norm = k == 0 ? kDefOF : k == 1 ? kDefML : kDefLL;
+    const int def_max = k == 0 ? 28 : k == 1 ? 52 : 35, def_log = k == 0 ? 5 : 6, max_log = k == 0 ? 8 : 9;
+    int max_symbol = k == 0 ? 31 : def_max;
+    while (counts[max_symbol] == 0) max_symbol--;
+    int largest = 0;
+    for (int i = 0; i <= max_symbol; i++) largest = max(largest, counts[i]);
+    const bool default_allowed = k != 0 || max_symbol < 28;        // :141
+    const int mode = select_seq_encoding(largest, nseq, def_log, default_allowed);
+    uint8_t spread[512];
+    int32_t cumul[56];
+    int table_log = def_log, desc = 0;
+    if (mode == 1) {
+        // FseCompressionTable.initializeRleTable (:41-50): one symbol, zero bits per step
+        sm.tdesc[k][0] = (uint8_t) max_symbol;
+        desc = 1;
+        table_log = 0;
+        nx[0] = 0; nx[1] = 0;
+        dnb[max_symbol] = 0; dfs[max_symbol] = 0;
+    }
+    else if (mode == 0) fse_build_ctable(nx, dnb, dfs, def_norm, def_max, def_log, spread, cumul);
+    else {
+        int16_t norm[56];
+        table_log = fse_optimal_table_log(max_log, nseq, max_symbol);
+        int total = nseq;
+        if (counts[last_code] > 1) { counts[last_code]--; total--; }
+        fse_normalize(norm, table_log, counts, total, max_symbol);
+        fse_build_ctable(nx, dnb, dfs, norm, max_symbol, table_log, spread, cumul);
+        desc = fse_write_ncount(sm.tdesc[k], (int) sizeof(sm.tdesc[k]), norm, max_symbol, table_log);
+    }
+    sm.v[V_MODE_OF + k] = mode;
+    sm.v[V_LOG_OF + k] = table_log;
+    sm.v[V_DESC_OF + k] = desc;
+}
+
 // OR `nbits` bits of `value` into a zero-initialised little-endian bit buffer at bit position `pos`
 __device__ __forceinline__ void or_bits(uint32_t *buf, uint32_t pos, uint64_t value, int nbits)
 {
@@ -280,7 +353,8 @@ __device__ __forceinline__ void block_copy(uint8_t *dst, const uint8_t *src, int
 
 __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uint8_t *scratch_base, const int64_t *frame_hashes)
 {
-    __shared__ EncSmem sm;
+    extern __shared__ __align__(16) uint8_t zenc_smem[];
+    EncSmem &sm = *reinterpret_cast<EncSmem *>(zenc_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *scratch = scratch_base + (int64_t) blockIdx.x * kScratchPerCta;
     uint64_t *seqs = reinterpret_cast<uint64_t *>(scratch);                              // [4][kMaxSeqQ]
@@ -289,21 +363,11 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
     uint32_t *stage = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(sbits) + (int64_t) 3 * kMaxSeq * 2);   // 4 stream stages + seq stage
     uint32_t *seq_stage = stage + 4 * kStreamStage / 4;
 
-    // predefined FSE encode tables, once per CTA
-    if (tid < 3) {
-        uint8_t spread[64];
-        int32_t cumul[64];
-        if (tid == 0) fse_build_ctable(sm.ll_next, sm.ll_dnb, sm.ll_dfs, kDefLL, 35, 6, spread, cumul);
-        else if (tid == 1) fse_build_ctable(sm.ml_next, sm.ml_dnb, sm.ml_dfs, kDefML, 52, 6, spread, cumul);
-        else fse_build_ctable(sm.of_next, sm.of_dnb, sm.of_dfs, kDefOF, 28, 5, spread, cumul);
-    }
-    __syncthreads();
-
     for (;;) {
         __syncthreads();
-        if (tid == 0) sm.v[23] = (int32_t) atomicAdd(b.work_counter, 1u);
+        if (tid == 0) sm.v[31] = (int32_t) atomicAdd(b.work_counter, 1u);
         __syncthreads();
-        const unsigned int idx = (unsigned int) sm.v[23];
+        const unsigned int idx = (unsigned int) sm.v[31];
         if ((int64_t) idx >= b.n) break;
         const uint8_t *in = b.src + b.src_off[idx];
         const int64_t in_len = b.src_len[idx];
@@ -331,7 +395,10 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
             op = 5 + (single_segment ? 0 : 1) + (cs_desc == 0 ? (single_segment ? 1 : 0) : (cs_desc == 1 ? 2 : 4));
         }
         // frame checksum: XXH64 of the whole input, computed for the batch by xxh64_kernel before this kernel
-        if (tid == 0) sm.v[V_CHECKSUM] = (int32_t) (uint32_t) (uint64_t) frame_hashes[idx];
+        if (tid == 0) {
+            sm.v[V_CHECKSUM] = (int32_t) (uint32_t) (uint64_t) frame_hashes[idx];
+            sm.v[V_REP1] = 1; sm.v[V_REP2] = 4; sm.v[V_REP3] = 8;   // repeated offsets at the start of a frame (RepeatedOffsets.java:18-19 + RFC 8878)
+        }
 
         int64_t block_start = 0;
         bool last_block;
@@ -345,32 +412,72 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
 
             if (bl >= 16) {
                 // ================= 1. match finding =================
-                for (int i = tid; i < (1 << kHashLog); i += kThreads) sm.u.hash[i] = 0xFFFFFFFFu;
+                {
+                    uint16_t *tz = &sm.u.t.inc[0][0];      // inc and fin are contiguous
+                    for (int i = tid; i < (kNQ << kShortLog) + (kNQ << kLongLog); i += kThreads) tz[i] = kEmpty16;
+                }
                 __syncthreads();
                 {
-                    const int q = ((bl + kNQ - 1) / kNQ + 31) & ~31;
+                    const int q = ((bl + kNQ - 1) / kNQ + 31) & ~31;        // <= 16384: positions inside a sub-range fit 14 bits
                     const int qs = min(q * warp, bl), qe = min(qs + q, bl);
+                    // ---- pass A: the long table of this sub-range (last position of every 6-byte value) ----
+                    {
+                        uint16_t *fin = sm.u.t.fin[warp];
+                        const int lim = min(qe, bl - 8);                   // 8 readable bytes at every hashed position
+                        for (int base = qs; base < lim; base += 32) {
+                            const int p = base + lane;
+                            uint32_t h = 0, slot = 0xFFFFFFFFu - (uint32_t) lane;   // idle lanes: distinct dummies
+                            if (p < lim) { h = zenc_long_hash(ld_u64_unaligned(blk + p)); slot = h & ((1u << kLongLog) - 1); }
+                            const unsigned peers = __match_any_sync(kFull, slot);   // equal slots in one step: the highest position wins
+                            if (p < lim && lane == 31 - __clz(peers)) fin[slot] = (uint16_t) ((uint32_t) (p - qs) | ((h >> kLongLog) << 14));
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                    // ---- pass B: greedy parse of the sub-range, 32 positions per step ----
+                    uint16_t *inc = sm.u.t.inc[warp];
                     uint64_t *my = seqs + (int64_t) warp * kMaxSeqQ;
                     int count = 0, anchor = qs, pos = qs;
-                    const int probe_limit = min(qe - 3, bl - 4);      // a match (>= 4 bytes) must end inside its quarter
+                    int rep1 = 0, rep2 = 0;                                  // the two most recent offsets of this parse (0: none yet)
+                    const int probe_limit = min(qe - 3, bl - 8);             // a match (>= 4 bytes) ends inside its sub-range
                     while (pos < probe_limit) {
                         const int p = pos + lane;
-                        bool hit = false;
-                        uint32_t cand = 0xFFFFFFFFu, cur = 0;
-                        if (p < probe_limit) {
-                            cur = ld_u32_unaligned(blk + p);
-                            const uint32_t h = zenc_slot(cur, warp);
-                            cand = sm.u.hash[h];
-                            if (cand < (uint32_t) p && ld_u32_unaligned(blk + cand) == cur) hit = true;
+                        const bool live = p < probe_limit;
+                        int cand = -1;
+                        uint32_t sslot = 0xFFFFFFFFu - (uint32_t) lane;
+                        if (live) {
+                            const uint64_t cur8 = ld_u64_unaligned(blk + p);
+                            const uint32_t cur = (uint32_t) cur8;
+                            sslot = zenc_short_slot(cur);
+                            if (rep1 && p >= rep1 && ld_u32_unaligned(blk + (p - rep1)) == cur) cand = p - rep1;
+                            else if (rep2 && p >= rep2 && ld_u32_unaligned(blk + (p - rep2)) == cur) cand = p - rep2;
+                            else {
+                                const uint32_t e = inc[sslot];
+                                if (e != kEmpty16 && qs + (int) e < p && ld_u32_unaligned(blk + (qs + (int) e)) == cur) cand = qs + (int) e;
+                                else {
+                                    const uint32_t h = zenc_long_hash(cur8);
+                                    const uint32_t ls = h & ((1u << kLongLog) - 1), tag = h >> kLongLog;
+                                    for (int k = 1; k <= kPrevTables && k <= warp; k++) {
+                                        const uint32_t f = sm.u.t.fin[warp - k][ls];
+                                        if (f != kEmpty16 && (f >> 14) == tag) {
+                                            const int c = q * (warp - k) + (int) (f & 0x3FFFu);
+                                            if (((ld_u64_unaligned(blk + c) ^ cur8) << 16) == 0) { cand = c; break; }
+                                        }
+                                    }
+                                }
+                            }
                         }
-                        __syncwarp();
-                        const unsigned hits = __ballot_sync(kFull, hit);
+                        const unsigned hits = __ballot_sync(kFull, cand >= 0);
                         const int first_hit = hits ? __ffs(hits) - 1 : 31;
-                        if (p < probe_limit && lane <= first_hit) sm.u.hash[zenc_slot(cur, warp)] = (uint32_t) p;   // see lz4.cu
+                        // Insert after the lookups, and only positions up to the first match (see lz4.cu); of equal slots in one
+                        // step the highest position wins, so the table -- and with it the output -- does not depend on timing.
+                        const bool ins = live && lane <= first_hit;
+                        const unsigned peers = __match_any_sync(kFull, ins ? sslot : 0xFFFFFFFFu - (uint32_t) lane);
+                        if (ins && lane == 31 - __clz(peers)) inc[sslot] = (uint16_t) (p - qs);
+                        __syncwarp();
                         if (hits == 0) { pos += 32; continue; }
-                        const int first = __ffs(hits) - 1;
-                        int mpos = pos + first;
-                        int ref = (int) __shfl_sync(kFull, cand, first);
+                        int mpos = pos + first_hit;
+                        int ref = __shfl_sync(kFull, cand, first_hit);
                         while (mpos > anchor && ref > 0 && blk[mpos - 1] == blk[ref - 1]) { --mpos; --ref; }
                         int mlen = 4;
                         for (;;) {
@@ -381,8 +488,10 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                             mlen += __ffs(~eq) - 1;
                             break;
                         }
-                        if (lane == 0) my[count] = pack_seq((uint32_t) (mpos - anchor), (uint32_t) mlen, (uint32_t) (mpos - ref));
+                        const int off = mpos - ref;
+                        if (lane == 0) my[count] = pack_seq((uint32_t) (mpos - anchor), (uint32_t) mlen, (uint32_t) off);
                         count++;
+                        if (off != rep1) { rep2 = rep1; rep1 = off; }
                         pos = mpos + mlen;
                         anchor = pos;
                     }
@@ -410,12 +519,52 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 for (int i = tid; i < 256; i += kThreads) sm.hist[i] = 0;
                 __syncthreads();
                 const int nseq = sm.v[V_NSEQ], last_lit = sm.v[V_LASTLIT];
-                auto seq_at = [&](int i) -> uint64_t {
+                auto seq_ptr = [&](int i) -> uint64_t * {
                     int w = 0;
 #pragma unroll
                     for (int k = 1; k < kNQ; k++) w += (i >= sm.qbase[k]);
-                    return seqs[(int64_t) w * kMaxSeqQ + (i - sm.qbase[w])];
+                    return seqs + ((int64_t) w * kMaxSeqQ + (i - sm.qbase[w]));
                 };
+                auto seq_at = [&](int i) -> uint64_t { return *seq_ptr(i); };
+                // ================= 2b. repeated offsets (RFC 8878 3.1.1.5, RepeatedOffsets.java:16-49) =================
+                // One thread walks the list with the decoder's history and turns every offset into its offset VALUE: 1..3 for a
+                // repeat code, offset + 3 otherwise.  The list passes through shared memory in tiles (the match tables are free now).
+                {
+                    constexpr int kTile = (int) (sizeof(sm.u.rep) / 4);
+                    if (tid == 0) { sm.v[V_REPT1] = sm.v[V_REP1]; sm.v[V_REPT2] = sm.v[V_REP2]; sm.v[V_REPT3] = sm.v[V_REP3]; }
+                    for (int t0 = 0; t0 < nseq; t0 += kTile) {
+                        const int tn = min(kTile, nseq - t0);
+                        __syncthreads();
+                        for (int i = tid; i < tn; i += kThreads) { const uint64_t sq = seq_at(t0 + i); sm.u.rep[i] = seq_off(sq) | (seq_ll(sq) ? 0x80000000u : 0u); }
+                        __syncthreads();
+                        if (tid == 0) {
+                            int r1 = sm.v[V_REPT1], r2 = sm.v[V_REPT2], r3 = sm.v[V_REPT3];
+                            for (int i = 0; i < tn; i++) {
+                                const uint32_t e = sm.u.rep[i];
+                                const int o = (int) (e & 0x7FFFFFFFu);
+                                uint32_t val = (uint32_t) o + 3;
+                                if (e >> 31) {                      // literals in front of the match
+                                    if (o == r1) val = 1;
+                                    else if (o == r2) { val = 2; r2 = r1; r1 = o; }
+                                    else { if (o == r3) val = 3; r3 = r2; r2 = r1; r1 = o; }
+                                }
+                                else {                              // no literals: the codes mean rep2, rep3, rep1 - 1
+                                    if (o == r2) { val = 1; r2 = r1; r1 = o; }
+                                    else { if (o == r3) val = 2; else if (o == r1 - 1) val = 3; r3 = r2; r2 = r1; r1 = o; }
+                                }
+                                sm.u.rep[i] = val;
+                            }
+                            sm.v[V_REPT1] = r1; sm.v[V_REPT2] = r2; sm.v[V_REPT3] = r3;
+                        }
+                        __syncthreads();
+                        for (int i = tid; i < tn; i += kThreads) {
+                            uint64_t *sp = seq_ptr(t0 + i);
+                            const uint64_t sq = *sp;
+                            *sp = pack_seq(seq_ll(sq), seq_ml(sq), sm.u.rep[i]);
+                        }
+                    }
+                    __syncthreads();
+                }
                 const int chunk = (nseq + kThreads - 1) / kThreads;
                 const int c0 = min(tid * chunk, nseq), c1 = min(c0 + chunk, nseq);
                 int my_ll = 0, my_all = 0;
@@ -502,40 +651,55 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 else if (lit_mode == 1) { lit_header = 1 + (nlit > 31) + (nlit > 4095); lit_section = lit_header + 1; }
 
                 // ================= 4. sequences section planning =================
-                int seq_header = nseq == 0 ? 1 : (nseq < 0x7F ? 1 : (nseq < 0x7F00 ? 2 : 3)) + 1;
+                int seq_header = 1;       // nseq == 0: just the count byte
                 int seq_bytes = 0;
                 if (nseq > 0) {
-                    // three threads walk the three FSE state chains from the last sequence to the first
+                    // code histograms of the three streams
+                    for (int i = tid; i < 3 * 56; i += kThreads) (&sm.chist[0][0])[i] = 0;
+                    __syncthreads();
+                    for (int i = c0; i < c1; i++) {
+                        const uint64_t s = seq_at(i);
+                        atomicAdd(&sm.chist[0][highbit(seq_off(s))], 1);
+                        atomicAdd(&sm.chist[1][ml_code_of(seq_ml(s) - 3)], 1);
+                        atomicAdd(&sm.chist[2][ll_code_of(seq_ll(s))], 1);
+                    }
+                    __syncthreads();
+                    // three threads: table selection + construction, then the FSE state chain of their stream from the last
+                    // sequence to the first (SequenceEncoder.encodeSequences :228-297)
                     if (tid == 0 || tid == 32 || tid == 64) {
                         const int k = tid >> 5;   // 0 OF, 1 ML, 2 LL
+                        auto code_of = [&](uint64_t s) { return k == 0 ? highbit(seq_off(s)) : k == 1 ? ml_code_of(seq_ml(s) - 3) : ll_code_of(seq_ll(s)); };
+                        const int last_code = code_of(seq_at(nseq - 1));
+                        build_seq_table(sm, k, nseq, last_code);
                         const uint16_t *nx = k == 0 ? sm.of_next : k == 1 ? sm.ml_next : sm.ll_next;
                         const int32_t *dnb = k == 0 ? sm.of_dnb : k == 1 ? sm.ml_dnb : sm.ll_dnb;
                         const int32_t *dfs = k == 0 ? sm.of_dfs : k == 1 ? sm.ml_dfs : sm.ll_dfs;
                         uint16_t *sb = sbits + (int64_t) k * kMaxSeq;
-                        auto code_of = [&](uint64_t s) { return k == 0 ? highbit(seq_off(s) + 3) : k == 1 ? ml_code_of(seq_ml(s) - 3) : ll_code_of(seq_ll(s)); };
-                        int state = fse_begin(nx, dnb, dfs, code_of(seq_at(nseq - 1)));
+                        int state = sm.v[V_MODE_OF + k] == 1 ? 0 : fse_begin(nx, dnb, dfs, last_code);
                         sb[nseq - 1] = 0;
                         for (int i = nseq - 2; i >= 0; i--) {
                             const int code = code_of(seq_at(i));
                             const int nb = (int) ((uint32_t) (state + dnb[code]) >> 16);
-                            sb[i] = (uint16_t) ((state & ((1 << nb) - 1)) | (nb << 8));
+                            sb[i] = (uint16_t) ((state & ((1 << nb) - 1)) | (nb << 12));
                             state = nx[(state >> nb) + dfs[code]];
                         }
                         sm.v[V_FINAL_OF + k] = state;
                     }
                     __syncthreads();
+                    const int log_of = sm.v[V_LOG_OF], log_ml = sm.v[V_LOG_ML], log_ll = sm.v[V_LOG_LL];
+                    seq_header = (nseq < 0x7F ? 1 : (nseq < 0x7F00 ? 2 : 3)) + 1 + sm.v[V_DESC_LL] + sm.v[V_DESC_OF] + sm.v[V_DESC_ML];
                     // bits per sequence, reverse prefix sums (encode order is last -> first)
                     int my_bits = 0;
                     for (int i = c0; i < c1; i++) {
                         const uint64_t s = seq_at(i);
-                        const int llc = ll_code_of(seq_ll(s)), mlc = ml_code_of(seq_ml(s) - 3), ofc = highbit(seq_off(s) + 3);
-                        my_bits += kLLBits[llc] + kMLBits[mlc] + ofc + (sbits[i] >> 8) + (sbits[kMaxSeq + i] >> 8) + (sbits[2 * kMaxSeq + i] >> 8);
+                        const int llc = ll_code_of(seq_ll(s)), mlc = ml_code_of(seq_ml(s) - 3), ofc = highbit(seq_off(s));
+                        my_bits += kLLBits[llc] + kMLBits[mlc] + ofc + (sbits[i] >> 12) + (sbits[kMaxSeq + i] >> 12) + (sbits[2 * kMaxSeq + i] >> 12);
                     }
                     int total_bits;
                     const int before = block_scan_excl(sm, my_bits, &total_bits);
                     const int my_start = total_bits - before - my_bits;   // bits emitted before this thread's chunk in encode order
                     if (tid == 0) sm.v[V_SEQ_TOTAL_BITS] = total_bits;
-                    seq_bytes = (total_bits + 6 + 5 + 6 + 1 + 7) >> 3;
+                    seq_bytes = (total_bits + log_ml + log_of + log_ll + 1 + 7) >> 3;
                     const int seq_section_try = seq_header + seq_bytes;
                     // ================= 5. decide, then emit =================
                     const int payload = lit_section + seq_section_try;
@@ -546,28 +710,28 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         uint32_t bitpos = (uint32_t) my_start;
                         for (int i = c1 - 1; i >= c0; i--) {
                             const uint64_t s = seq_at(i);
-                            const uint32_t ll = seq_ll(s), mlb = seq_ml(s) - 3, ofv = seq_off(s) + 3;
+                            const uint32_t ll = seq_ll(s), mlb = seq_ml(s) - 3, ofv = seq_off(s);
                             const int llc = ll_code_of(ll), mlc = ml_code_of(mlb), ofc = highbit(ofv);
                             const int llb = kLLBits[llc], mlbits = kMLBits[mlc];
                             const uint32_t s_of = sbits[i], s_ml = sbits[kMaxSeq + i], s_ll = sbits[2 * kMaxSeq + i];
-                            or_bits(seq_stage, bitpos, s_of & 0xFF, (int) (s_of >> 8)); bitpos += s_of >> 8;
-                            or_bits(seq_stage, bitpos, s_ml & 0xFF, (int) (s_ml >> 8)); bitpos += s_ml >> 8;
-                            or_bits(seq_stage, bitpos, s_ll & 0xFF, (int) (s_ll >> 8)); bitpos += s_ll >> 8;
+                            or_bits(seq_stage, bitpos, s_of & 0xFFF, (int) (s_of >> 12)); bitpos += s_of >> 12;
+                            or_bits(seq_stage, bitpos, s_ml & 0xFFF, (int) (s_ml >> 12)); bitpos += s_ml >> 12;
+                            or_bits(seq_stage, bitpos, s_ll & 0xFFF, (int) (s_ll >> 12)); bitpos += s_ll >> 12;
                             or_bits(seq_stage, bitpos, ll & ((1u << llb) - 1), llb); bitpos += llb;
                             or_bits(seq_stage, bitpos, mlb & ((1u << mlbits) - 1), mlbits); bitpos += mlbits;
                             or_bits(seq_stage, bitpos, ofv & ((1u << ofc) - 1), ofc); bitpos += ofc;
                         }
                         if (tid == 0) {
                             uint32_t bp = (uint32_t) total_bits;
-                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_ML] & 63, 6); bp += 6;
-                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_OF] & 31, 5); bp += 5;
-                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_LL] & 63, 6); bp += 6;
+                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_ML] & ((1u << log_ml) - 1), log_ml); bp += log_ml;
+                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_OF] & ((1u << log_of) - 1), log_of); bp += log_of;
+                            or_bits(seq_stage, bp, (uint32_t) sm.v[V_FINAL_LL] & ((1u << log_ll) - 1), log_ll); bp += log_ll;
                             or_bits(seq_stage, bp, 1, 1);
                         }
                     }
                 }
                 else {
-                    compressed = lit_section + seq_header <= bl - ((bl >> 6) + 2);
+                    compressed = lit_section + seq_header <= bl - ((bl >> 6) + 2);   // no sequences: literals + the count byte
                 }
                 __syncthreads();
                 if (compressed) {
@@ -651,7 +815,13 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         if (nseq < 0x7F) sq[p++] = (uint8_t) nseq;
                         else if (nseq < 0x7F00) { sq[p++] = (uint8_t) ((nseq >> 8) | 0x80); sq[p++] = (uint8_t) nseq; }
                         else { sq[p++] = 0xFF; uint32_t v = (uint32_t) (nseq - 0x7F00); sq[p++] = (uint8_t) v; sq[p++] = (uint8_t) (v >> 8); }
-                        if (nseq > 0) sq[p++] = 0;   // all three tables predefined (SEQUENCE_ENCODING_BASIC)
+                        if (nseq > 0) {
+                            // encoding types (:205), then the table descriptions in the order LL, OF, ML (:96-199)
+                            sq[p++] = (uint8_t) ((sm.v[V_MODE_LL] << 6) | (sm.v[V_MODE_OF] << 4) | (sm.v[V_MODE_ML] << 2));
+                            for (int i = 0; i < sm.v[V_DESC_LL]; i++) sq[p++] = sm.tdesc[2][i];
+                            for (int i = 0; i < sm.v[V_DESC_OF]; i++) sq[p++] = sm.tdesc[0][i];
+                            for (int i = 0; i < sm.v[V_DESC_ML]; i++) sq[p++] = sm.tdesc[1][i];
+                        }
                     }
                     if (nseq > 0) block_copy<true>(sq + seq_header, reinterpret_cast<const uint8_t *>(seq_stage), seq_bytes);
                     block_bytes = lit_section + seq_header + seq_bytes;
@@ -664,6 +834,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
             if (tid == 0) {
                 // 3-byte block header: last (1) | type (2) | size (21)  (ZstdFrameCompressor.writeCompressedBlock :181-204)
                 const uint32_t h = (last_block ? 1u : 0u) | ((compressed ? 2u : 0u) << 1) | ((uint32_t) block_bytes << 3);
+                // the decoder only sees the sequences of compressed blocks: commit the offset history for those (CompressionContext.commit)
+                if (compressed) { sm.v[V_REP1] = sm.v[V_REPT1]; sm.v[V_REP2] = sm.v[V_REPT2]; sm.v[V_REP3] = sm.v[V_REPT3]; }
                 out[op] = (uint8_t) h; out[op + 1] = (uint8_t) (h >> 8); out[op + 2] = (uint8_t) (h >> 16);
             }
             op += 3 + block_bytes;
@@ -684,7 +856,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
 
 }  // namespace
 
-static int64_t zstd_enc_grid(int sm_count) { return (int64_t) sm_count * 5; }
+static int64_t zstd_enc_grid(int sm_count) { return (int64_t) sm_count * 4; }   // 56 KiB of shared memory and 64 registers x 256 threads per CTA
 
 int64_t acc_zstd_enc_scratch_bytes(int sm_count, int64_t n) { return zstd_enc_grid(sm_count) * kScratchPerCta + n * 8 + 256; }
 
@@ -701,5 +873,6 @@ void acc_launch_zstd_compress(const AccBatch &b, int sm_count, cudaStream_t st, 
     hb.out_len = hashes;
     hb.status = nullptr;
     acc_launch_xxh64(hb, 0, sm_count, st);
-    zstd_compress_kernel<<<(unsigned) ctas, kThreads, 0, st>>>(b, (uint8_t *) scratch, hashes);
+    cudaFuncSetAttribute(zstd_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EncSmem));
+    zstd_compress_kernel<<<(unsigned) ctas, kThreads, sizeof(EncSmem), st>>>(b, (uint8_t *) scratch, hashes);
 }
