@@ -47,6 +47,7 @@ def lib():
         "acc_sm_count": (i32, [vp]),
         "acc_kernel_launches": (i64, [vp]),
         "acc_set_tuning": (i32, [vp, i32, i32]),
+        "acc_get_stats": (i32, [vp, pi64, i32]),
         "acc_lz4_compress_bound": (i64, [i64]),
         "acc_snappy_compress_bound": (i64, [i64]),
         "acc_zstd_compress_bound": (i64, [i64]),

@@ -177,6 +177,7 @@ class SnappyCudaDecompressor(Decompressor):
     def getUncompressedLength(self, compressed, compressedOffset=0):
         """SnappyDecompressor.getUncompressedLength (snappy/SnappyDecompressor.java:22)."""
         src = _as_array(compressed)
+        _verify_range(src, compressedOffset, 0)      # the reference bounds the varint read by compressed.length
         off = C.c_int64(0)
         r = self._L.acc_snappy_uncompressed_length(src.ctypes.data + compressedOffset, src.size - compressedOffset, C.byref(off))
         if r < 0:
@@ -252,6 +253,14 @@ class BatchEngine:
 
     def set_tuning(self, key, value):
         return self._L.acc_set_tuning(self._ctx.handle, key, value)
+
+    STAT_NAMES = ("batches", "blocks", "launches", "host_calls", "h2d_bytes", "d2h_bytes", "last_call_us", "total_call_us")
+
+    def stats(self):
+        """acc_get_stats: counters of this context since it was created (include/aircompress_cuda.h ACC_STAT_*)."""
+        buf = (C.c_int64 * len(self.STAT_NAMES))()
+        n = self._L.acc_get_stats(self._ctx.handle, buf, len(self.STAT_NAMES))
+        return {self.STAT_NAMES[i]: int(buf[i]) for i in range(n)}
 
     def run_host(self, op, src, src_off, src_len, dst, dst_off, dst_cap):
         """numpy in/out. Returns (out_len, status) arrays."""

@@ -3,6 +3,7 @@
 // There is deliberately no CPU code path for any codec in this file: every compress / decompress /
 // hash request becomes a kernel launch, and when no GPU is usable acc_init() fails.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,11 +24,18 @@ struct acc_ctx {
     int64_t *d_idx = nullptr; int64_t d_idx_cap = 0;   // src_off | src_len | dst_off | dst_cap | out_len, then status
     void *d_scratch = nullptr; int64_t d_scratch_cap = 0;
     int64_t *h_idx = nullptr; int64_t h_idx_cap = 0;   // pinned mirror of d_idx
+    uint8_t *h_stage = nullptr; int64_t h_stage_cap = 0;   // pinned staging of the single-block calls (input, then the output window)
     int32_t last_status = 0;
     int64_t last_offset = 0;
     int64_t launches = 0;
+    // everything a context owns on the device (scratch, work counters, staging) is shared by its batches: work enqueued on
+    // a different stream than the previous batch first waits for that batch (ev_order), so batches of one context never
+    // overlap -- contexts are the unit of concurrency (one per thread, like the reference's codec objects)
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+    cudaEvent_t ev_order = nullptr;
+    int64_t stats[ACC_STATS_WORDS] = {};
     int tuning_ctas_per_sm = 0;
-    int tuning_decoder = 0;   // reserved (one LZ4 / Snappy decode kernel ships)
     int tuning_pipeline = 0;  // host-pointer batches: 0 = auto, 1 = never split, k > 1 = split into k chunks
     // copy streams + events of the pipelined host-pointer path (created on first use)
     static constexpr int kMaxChunks = 16;
@@ -67,6 +75,7 @@ acc_ctx *acc_init(int32_t device)
     ok = ok && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&c->counters, sizeof(unsigned int) * acc_ctx::kCounters) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         t_init_error = ACC_STATUS(ACC_E_CUDA, (int) cudaGetLastError());
         delete c;
@@ -85,8 +94,10 @@ void acc_destroy(acc_ctx *c)
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int i = 0; i < acc_ctx::kMaxChunks; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]); }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     cudaFree(c->counters); cudaFree(c->d_src); cudaFree(c->d_dst); cudaFree(c->d_idx); cudaFree(c->d_scratch);
     if (c->h_idx) cudaFreeHost(c->h_idx);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     delete c;
 }
 
@@ -109,11 +120,19 @@ int32_t acc_last_error(acc_ctx *c, int64_t *offset)
 int32_t acc_sm_count(acc_ctx *c) { return c ? c->sm_count : 0; }
 int64_t acc_kernel_launches(acc_ctx *c) { return c ? c->launches : 0; }
 
+int32_t acc_get_stats(acc_ctx *c, int64_t *out, int32_t words)
+{
+    if (!c || !out || words < 0) return 0;
+    c->stats[ACC_STAT_LAUNCHES] = c->launches;
+    const int32_t n = words < ACC_STATS_WORDS ? words : ACC_STATS_WORDS;
+    for (int32_t i = 0; i < n; i++) out[i] = c->stats[i];
+    return n;
+}
+
 int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
 {
     if (!c) return 0;
     if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
-    if (key == 1) { int prev = c->tuning_decoder; c->tuning_decoder = value; return prev; }
     if (key == 3) { int prev = c->tuning_pipeline; c->tuning_pipeline = value; return prev; }
     return 0;
 }
@@ -188,12 +207,13 @@ static bool grow(void **p, int64_t *cap, int64_t need, bool host)
 // enqueue one batch kernel; all pointers in b are device pointers
 static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint64_t seed)
 {
+    if (c->have_last && c->last_stream != st) cudaStreamWaitEvent(st, c->ev_order, 0);   // the previous batch of this context ran elsewhere
     b.work_counter = next_counter(c, st);
     switch (op) {
         case ACC_OP_LZ4_COMPRESS: acc_launch_lz4_compress(b, c->sm_count, st, next_counter(c, st)); c->launches++; break;
-        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, c->tuning_decoder, st); break;
+        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
         case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
-        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, c->tuning_decoder, st); break;
+        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
         case ACC_OP_ZSTD_COMPRESS:
         case ACC_OP_ZSTD_DECOMPRESS: {
@@ -206,6 +226,11 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
         default: return -ACC_STATUS(ACC_E_ARGUMENT, 0);
     }
     c->launches++;
+    cudaEventRecord(c->ev_order, st);
+    c->last_stream = st;
+    c->have_last = true;
+    c->stats[ACC_STAT_BATCHES]++;
+    c->stats[ACC_STAT_BLOCKS] += b.n;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -ACC_STATUS(ACC_E_CUDA, (int) e);
     return 0;
@@ -328,6 +353,40 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
         h[2 * n + i] = has_dst ? dst_off[i] - dst_lo + dst_pad : 0;
         h[3 * n + i] = has_dst ? dst_cap[i] : 0;
     }
+    const auto t_call = std::chrono::steady_clock::now();
+    auto account = [&](int64_t d2h) {
+        c->stats[ACC_STAT_HOST_CALLS]++;
+        c->stats[ACC_STAT_H2D_BYTES] += src_bytes + 4 * n * 8;
+        c->stats[ACC_STAT_D2H_BYTES] += d2h + n * 12;
+        const int64_t us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_call).count();
+        c->stats[ACC_STAT_LAST_CALL_US] = us;
+        c->stats[ACC_STAT_TOTAL_CALL_US] += us;
+    };
+    if (n == 1 && src_bytes + dst_bytes <= (8 << 20)) {
+        // ---- single block (the Java-shaped entry points): pageable caller memory is staged through a pinned buffer, the
+        // whole output window comes back in the same stream as the result words: ONE synchronisation per call, and only the
+        // bytes produced are copied into the caller's buffer (bytes beyond the returned length stay untouched, like with
+        // the reference codecs)
+        if (!grow((void **) &c->h_stage, &c->h_stage_cap, src_bytes + dst_bytes + 64, true)) return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
+        if (src_bytes > 0) memcpy(c->h_stage, (const uint8_t *) src_base + src_lo, (size_t) src_bytes);
+        CU_TRY(cudaMemcpyAsync(c->d_idx, h, (size_t) (4 * 8), cudaMemcpyHostToDevice, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        if (src_bytes > 0)
+            CU_TRY(cudaMemcpyAsync(c->d_src + src_pad, c->h_stage, (size_t) src_bytes, cudaMemcpyHostToDevice, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        AccBatch b1{c->d_src, c->d_idx, c->d_idx + 1, c->d_dst, c->d_idx + 2, c->d_idx + 3, c->d_idx + 4, (int32_t *) (c->d_idx + 5), 1, nullptr};
+        const int32_t r1 = enqueue(c, op, b1, st, seed);
+        if (r1 != 0) return r1;
+        CU_TRY(cudaMemcpyAsync(h + 4, c->d_idx + 4, (size_t) (8 + 4), cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        if (has_dst && dst_bytes > 0)
+            CU_TRY(cudaMemcpyAsync(c->h_stage + src_bytes, c->d_dst + dst_pad, (size_t) dst_bytes, cudaMemcpyDeviceToHost, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        CU_TRY(cudaStreamSynchronize(st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
+        const int64_t produced = h[4];
+        const int32_t stt = ((int32_t *) (h + 5))[0];
+        if (has_dst && stt == 0 && produced > 0) memcpy((uint8_t *) dst_base + dst_lo, c->h_stage + src_bytes, (size_t) (produced < dst_bytes ? produced : dst_bytes));
+        out_len[0] = produced;
+        if (status) status[0] = stt;
+        account(dst_bytes);
+        return 0;
+    }
     const int chunks = pipeline_chunks(c, n, src_bytes + dst_bytes, src_off);
     if (chunks > 1) {
         int32_t r = batch_host_pipelined(c, op, src_base, src_off, src_len, dst_base, dst_off, dst_cap, n, st, seed, chunks,
@@ -335,6 +394,7 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
         if (r != 0) return r;
         memcpy(out_len, h + 4 * n, (size_t) (n * 8));
         if (status) memcpy(status, h + 5 * n, (size_t) (n * 4));
+        account(dst_bytes);
         return 0;
     }
     CU_TRY(cudaMemcpyAsync(c->d_idx, h, (size_t) (4 * n * 8), cudaMemcpyHostToDevice, st), return -ACC_STATUS(ACC_E_CUDA, (int) e_));
@@ -371,6 +431,7 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
     }
     memcpy(out_len, h + 4 * n, (size_t) (n * 8));
     if (status) memcpy(status, h + 5 * n, (size_t) (n * 4));
+    account(dst_bytes);
     return 0;
 }
 

@@ -130,9 +130,9 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, int64_t offset, in
 }
 
 // kernel launchers implemented in the per-codec translation units
-void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st);
+void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st);
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter);
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st);
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st);
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st);
 void acc_launch_xxh64(const AccBatch &b, uint64_t seed, int sm_count, cudaStream_t st);
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes);

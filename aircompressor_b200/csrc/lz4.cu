@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
 
 }  // namespace
 
-void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
+void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     // warp-per-block step decoder: multi-sequence + medium steps, registers bounded for 8 resident CTAs (32 registers,
     // 64 warps per SM)

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
 
 }  // namespace
 
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, int version, cudaStream_t st)
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;

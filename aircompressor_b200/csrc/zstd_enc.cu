@@ -47,7 +47,8 @@ constexpr int kMaxSeqQ = kMaxBlock / kNQ / 4 + 16;       // sequences per sub-ra
 constexpr int kMaxSeq = kNQ * kMaxSeqQ;
 constexpr int kStreamStage = 48 * 1024;                  // staging bytes per Huffman stream (32768 symbols x 11 bits)
 constexpr int kSeqStage = kMaxBlock + 1024;              // staging bytes for the sequence bitstream
-constexpr int64_t kScratchPerCta = (int64_t) kMaxSeq * 8 + (kMaxBlock + 64) + (int64_t) 3 * kMaxSeq * 2 + 4 * kStreamStage + kSeqStage + 256;
+constexpr int64_t kScratchPerCta = (int64_t) kMaxSeq * 8 + (kMaxBlock + 64) + (int64_t) 3 * kMaxSeq * 2 + 4 * kStreamStage + kSeqStage + 256 +
+                                   (int64_t) kMaxSeq * 8 + (int64_t) kMaxSeq * 4;   // + compact sequence list + code words
 
 __device__ __forceinline__ uint32_t zenc_short_slot(uint32_t v) { return (v * 2654435761u) >> (32 - kShortLog); }
 // 6-byte hash (hash6 of DoubleFastBlockCompressor.java:216-256): slot in the low kLongLog bits, 2 tag bits above them
@@ -362,6 +363,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
     uint16_t *sbits = reinterpret_cast<uint16_t *>(lits + kMaxBlock + 64);               // [3][kMaxSeq] state bits of OF, ML, LL
     uint32_t *stage = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(sbits) + (int64_t) 3 * kMaxSeq * 2);   // 4 stream stages + seq stage
     uint32_t *seq_stage = stage + 4 * kStreamStage / 4;
+    uint64_t *seqc = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(seq_stage) + kSeqStage + 256);   // concatenated list, offsets as offset values
+    uint32_t *codew_g = reinterpret_cast<uint32_t *>(seqc + kMaxSeq);                                            // OF | ML << 8 | LL << 16 codes per sequence
 
     for (;;) {
         __syncthreads();
@@ -446,25 +449,39 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         int cand = -1;
                         uint32_t sslot = 0xFFFFFFFFu - (uint32_t) lane;
                         if (live) {
-                            const uint64_t cur8 = ld_u64_unaligned(blk + p);
+                            // every candidate's bytes are requested before the first comparison: the loads overlap instead of
+                            // forming a chain of dependent round trips
+                            const uint8_t *pp = blk + p;
+                            const uint64_t cur8 = ld_u64_unaligned(pp);
+                            const bool t1 = rep1 && p >= rep1, t2 = rep2 && p >= rep2;
+                            const uint32_t v1 = t1 ? ld_u32_unaligned(pp - rep1) : 0u, v2 = t2 ? ld_u32_unaligned(pp - rep2) : 0u;
                             const uint32_t cur = (uint32_t) cur8;
                             sslot = zenc_short_slot(cur);
-                            if (rep1 && p >= rep1 && ld_u32_unaligned(blk + (p - rep1)) == cur) cand = p - rep1;
-                            else if (rep2 && p >= rep2 && ld_u32_unaligned(blk + (p - rep2)) == cur) cand = p - rep2;
-                            else {
-                                const uint32_t e = inc[sslot];
-                                if (e != kEmpty16 && qs + (int) e < p && ld_u32_unaligned(blk + (qs + (int) e)) == cur) cand = qs + (int) e;
-                                else {
-                                    const uint32_t h = zenc_long_hash(cur8);
-                                    const uint32_t ls = h & ((1u << kLongLog) - 1), tag = h >> kLongLog;
-                                    for (int k = 1; k <= kPrevTables && k <= warp; k++) {
-                                        const uint32_t f = sm.u.t.fin[warp - k][ls];
-                                        if (f != kEmpty16 && (f >> 14) == tag) {
-                                            const int c = q * (warp - k) + (int) (f & 0x3FFFu);
-                                            if (((ld_u64_unaligned(blk + c) ^ cur8) << 16) == 0) { cand = c; break; }
-                                        }
+                            const uint32_t e = inc[sslot];
+                            const bool ti = e != kEmpty16 && qs + (int) e < p;
+                            const uint32_t vi = ti ? ld_u32_unaligned(blk + (qs + (int) e)) : 0u;
+                            const uint32_t h = zenc_long_hash(cur8);
+                            const uint32_t ls = h & ((1u << kLongLog) - 1), tag = h >> kLongLog;
+                            int cl[kPrevTables];
+                            uint64_t wl[kPrevTables];
+#pragma unroll
+                            for (int k = 1; k <= kPrevTables; k++) {
+                                cl[k - 1] = -1; wl[k - 1] = 0;
+                                if (k <= warp) {
+                                    const uint32_t f = sm.u.t.fin[warp - k][ls];
+                                    if (f != kEmpty16 && (f >> 14) == tag) {
+                                        cl[k - 1] = q * (warp - k) + (int) (f & 0x3FFFu);
+                                        wl[k - 1] = ld_u64_unaligned(blk + cl[k - 1]);
                                     }
                                 }
+                            }
+                            if (t1 && v1 == cur) cand = p - rep1;
+                            else if (t2 && v2 == cur) cand = p - rep2;
+                            else if (ti && vi == cur) cand = qs + (int) e;
+                            else {
+#pragma unroll
+                                for (int k = 0; k < kPrevTables; k++)
+                                    if (cand < 0 && cl[k] >= 0 && ((wl[k] ^ cur8) << 16) == 0) cand = cl[k];
                             }
                         }
                         const unsigned hits = __ballot_sync(kFull, cand >= 0);
@@ -519,23 +536,24 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 for (int i = tid; i < 256; i += kThreads) sm.hist[i] = 0;
                 __syncthreads();
                 const int nseq = sm.v[V_NSEQ], last_lit = sm.v[V_LASTLIT];
-                auto seq_ptr = [&](int i) -> uint64_t * {
+                auto seq_raw = [&](int i) -> uint64_t {       // sequence i of the eight per-warp lists
                     int w = 0;
 #pragma unroll
                     for (int k = 1; k < kNQ; k++) w += (i >= sm.qbase[k]);
-                    return seqs + ((int64_t) w * kMaxSeqQ + (i - sm.qbase[w]));
+                    return seqs[(int64_t) w * kMaxSeqQ + (i - sm.qbase[w])];
                 };
-                auto seq_at = [&](int i) -> uint64_t { return *seq_ptr(i); };
+                auto seq_at = [&](int i) -> uint64_t { return seqc[i]; };   // valid after the repeated-offset pass
                 // ================= 2b. repeated offsets (RFC 8878 3.1.1.5, RepeatedOffsets.java:16-49) =================
                 // One thread walks the list with the decoder's history and turns every offset into its offset VALUE: 1..3 for a
-                // repeat code, offset + 3 otherwise.  The list passes through shared memory in tiles (the match tables are free now).
+                // repeat code, offset + 3 otherwise.  The list passes through shared memory in tiles (the match tables are free now)
+                // and lands in one contiguous array.
                 {
                     constexpr int kTile = (int) (sizeof(sm.u.rep) / 4);
                     if (tid == 0) { sm.v[V_REPT1] = sm.v[V_REP1]; sm.v[V_REPT2] = sm.v[V_REP2]; sm.v[V_REPT3] = sm.v[V_REP3]; }
                     for (int t0 = 0; t0 < nseq; t0 += kTile) {
                         const int tn = min(kTile, nseq - t0);
                         __syncthreads();
-                        for (int i = tid; i < tn; i += kThreads) { const uint64_t sq = seq_at(t0 + i); sm.u.rep[i] = seq_off(sq) | (seq_ll(sq) ? 0x80000000u : 0u); }
+                        for (int i = tid; i < tn; i += kThreads) { const uint64_t sq = seq_raw(t0 + i); sm.u.rep[i] = seq_off(sq) | (seq_ll(sq) ? 0x80000000u : 0u); }
                         __syncthreads();
                         if (tid == 0) {
                             int r1 = sm.v[V_REPT1], r2 = sm.v[V_REPT2], r3 = sm.v[V_REPT3];
@@ -558,9 +576,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         }
                         __syncthreads();
                         for (int i = tid; i < tn; i += kThreads) {
-                            uint64_t *sp = seq_ptr(t0 + i);
-                            const uint64_t sq = *sp;
-                            *sp = pack_seq(seq_ll(sq), seq_ml(sq), sm.u.rep[i]);
+                            const uint64_t sq = seq_raw(t0 + i);
+                            seqc[t0 + i] = pack_seq(seq_ll(sq), seq_ml(sq), sm.u.rep[i]);   // the compact list every later stage reads
                         }
                     }
                     __syncthreads();
@@ -657,19 +674,24 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                     // code histograms of the three streams
                     for (int i = tid; i < 3 * 56; i += kThreads) (&sm.chist[0][0])[i] = 0;
                     __syncthreads();
-                    for (int i = c0; i < c1; i++) {
+                    // one word of codes per sequence, in shared memory when the list fits (the chain walkers below are serial:
+                    // their loads must be short)
+                    uint32_t *codew = nseq <= (int) (sizeof(sm.u.rep) / 4) ? sm.u.rep : codew_g;
+                    for (int i = tid; i < nseq; i += kThreads) {
                         const uint64_t s = seq_at(i);
-                        atomicAdd(&sm.chist[0][highbit(seq_off(s))], 1);
-                        atomicAdd(&sm.chist[1][ml_code_of(seq_ml(s) - 3)], 1);
-                        atomicAdd(&sm.chist[2][ll_code_of(seq_ll(s))], 1);
+                        const int ofc = highbit(seq_off(s)), mlc = ml_code_of(seq_ml(s) - 3), llc = ll_code_of(seq_ll(s));
+                        codew[i] = (uint32_t) ofc | ((uint32_t) mlc << 8) | ((uint32_t) llc << 16);
+                        atomicAdd(&sm.chist[0][ofc], 1);
+                        atomicAdd(&sm.chist[1][mlc], 1);
+                        atomicAdd(&sm.chist[2][llc], 1);
                     }
                     __syncthreads();
                     // three threads: table selection + construction, then the FSE state chain of their stream from the last
                     // sequence to the first (SequenceEncoder.encodeSequences :228-297)
                     if (tid == 0 || tid == 32 || tid == 64) {
                         const int k = tid >> 5;   // 0 OF, 1 ML, 2 LL
-                        auto code_of = [&](uint64_t s) { return k == 0 ? highbit(seq_off(s)) : k == 1 ? ml_code_of(seq_ml(s) - 3) : ll_code_of(seq_ll(s)); };
-                        const int last_code = code_of(seq_at(nseq - 1));
+                        auto code_at = [&](int i) { return (int) ((codew[i] >> (8 * k)) & 0xFF); };
+                        const int last_code = code_at(nseq - 1);
                         build_seq_table(sm, k, nseq, last_code);
                         const uint16_t *nx = k == 0 ? sm.of_next : k == 1 ? sm.ml_next : sm.ll_next;
                         const int32_t *dnb = k == 0 ? sm.of_dnb : k == 1 ? sm.ml_dnb : sm.ll_dnb;
@@ -678,7 +700,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         int state = sm.v[V_MODE_OF + k] == 1 ? 0 : fse_begin(nx, dnb, dfs, last_code);
                         sb[nseq - 1] = 0;
                         for (int i = nseq - 2; i >= 0; i--) {
-                            const int code = code_of(seq_at(i));
+                            const int code = code_at(i);
                             const int nb = (int) ((uint32_t) (state + dnb[code]) >> 16);
                             sb[i] = (uint16_t) ((state & ((1 << nb) - 1)) | (nb << 12));
                             state = nx[(state >> nb) + dfs[code]];
@@ -691,8 +713,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                     // bits per sequence, reverse prefix sums (encode order is last -> first)
                     int my_bits = 0;
                     for (int i = c0; i < c1; i++) {
-                        const uint64_t s = seq_at(i);
-                        const int llc = ll_code_of(seq_ll(s)), mlc = ml_code_of(seq_ml(s) - 3), ofc = highbit(seq_off(s));
+                        const uint32_t cw = codew[i];
+                        const int ofc = (int) (cw & 0xFF), mlc = (int) ((cw >> 8) & 0xFF), llc = (int) (cw >> 16);
                         my_bits += kLLBits[llc] + kMLBits[mlc] + ofc + (sbits[i] >> 12) + (sbits[kMaxSeq + i] >> 12) + (sbits[2 * kMaxSeq + i] >> 12);
                     }
                     int total_bits;
@@ -711,7 +733,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         for (int i = c1 - 1; i >= c0; i--) {
                             const uint64_t s = seq_at(i);
                             const uint32_t ll = seq_ll(s), mlb = seq_ml(s) - 3, ofv = seq_off(s);
-                            const int llc = ll_code_of(ll), mlc = ml_code_of(mlb), ofc = highbit(ofv);
+                            const uint32_t cw = codew[i];
+                            const int ofc = (int) (cw & 0xFF), mlc = (int) ((cw >> 8) & 0xFF), llc = (int) (cw >> 16);
                             const int llb = kLLBits[llc], mlbits = kMLBits[mlc];
                             const uint32_t s_of = sbits[i], s_ml = sbits[kMaxSeq + i], s_ll = sbits[2 * kMaxSeq + i];
                             or_bits(seq_stage, bitpos, s_of & 0xFFF, (int) (s_of >> 12)); bitpos += s_of >> 12;

@@ -142,8 +142,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_WORKLOADS = {}
+
+
 def build_workload(codec, block_kib, n_blocks, orc, threads):
     """Returns dict with host arrays: distinct blocks, their compressed streams (reference algorithm), tiling."""
+    key = (codec, block_kib)
+    if key in _WORKLOADS:
+        return dict(_WORKLOADS[key], n=n_blocks)
+    wl = _build_workload(codec, block_kib, n_blocks, orc, threads)
+    _WORKLOADS[key] = wl
+    return wl
+
+
+def _build_workload(codec, block_kib, n_blocks, orc, threads):
     label, pieces = benchdata.load_pieces()
     blocks = benchdata.cut_blocks(pieces, block_kib * 1024)
     raw, raw_off, raw_len = benchdata.pack(blocks)
@@ -251,6 +263,89 @@ def cpu_baseline_leg(args, wl, orc, op, n, threads):
     return cpu_baseline
 
 
+class DeviceRun:
+    """One (codec, op, block size, batch) workload resident in HBM, and the timing of its kernel launches."""
+
+    def __init__(self, acb, eng, orc, dev, codec, opname, block_kib, n, threads):
+        import torch
+        self.torch, self.eng, self.orc, self.dev = torch, eng, orc, dev
+        self.codec, self.opname, self.n = codec, opname, n
+        self.op = CODEC_OPS[(codec, opname)]
+        wl = self.wl = build_workload(codec, block_kib, n, orc, threads)
+
+        def to_dev_tiled(packed, off, ln):
+            reps, stride, stride_al, offs, lens = tile_index(off, ln, n)
+            one = torch.zeros(stride_al, dtype=torch.uint8, device=dev)
+            one[:stride] = torch.from_numpy(packed).to(dev)
+            buf = one.repeat(reps)
+            return buf, torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev), offs, lens
+
+        self.raw_d, self.raw_off_d, self.raw_len_d, self.raw_off_h, self.raw_len_h = to_dev_tiled(wl["raw"], wl["raw_off"], wl["raw_len"])
+        self.unc_bytes = int(self.raw_len_h.sum())
+        if opname == "hash":
+            self.src_d, self.src_off_d, self.src_len_d, self.src_off_h, self.src_len_h = self.raw_d, self.raw_off_d, self.raw_len_d, self.raw_off_h, self.raw_len_h
+            self.dst_d = torch.zeros(16, dtype=torch.uint8, device=dev)
+            self.dst_off_d = torch.zeros(n, dtype=torch.int64, device=dev)
+            self.dst_cap_d = torch.zeros(n, dtype=torch.int64, device=dev)
+            self.comp_bytes = 0
+        elif opname == "decompress":
+            self.src_d, self.src_off_d, self.src_len_d, self.src_off_h, self.src_len_h = to_dev_tiled(wl["comp"], wl["comp_off"], wl["comp_len"])
+            self.dst_d = torch.zeros_like(self.raw_d)
+            self.dst_off_d, self.dst_cap_d = self.raw_off_d, self.raw_len_d
+            self.comp_bytes = int(self.src_len_h.sum())
+        else:
+            self.src_d, self.src_off_d, self.src_len_d, self.src_off_h, self.src_len_h = self.raw_d, self.raw_off_d, self.raw_len_d, self.raw_off_h, self.raw_len_h
+            bound = int(getattr(acb.lib(), f"acc_{codec}_compress_bound")(int(self.raw_len_h.max())))
+            self.dst_d = torch.zeros(bound * n, dtype=torch.uint8, device=dev)
+            self.dst_off_d = torch.arange(n, dtype=torch.int64, device=dev) * bound
+            self.dst_cap_d = torch.full((n,), bound, dtype=torch.int64, device=dev)
+            self.comp_bytes = None
+        self.out_len_d = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.status_d = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def step(self):
+        st = self.torch.cuda.current_stream().cuda_stream
+        assert st != 0   # handle 0 would mean "the context's own stream" to acc_batch, which torch events cannot see
+        self.eng.run_device(self.op, self.src_d.data_ptr(), self.src_off_d.data_ptr(), self.src_len_d.data_ptr(), self.dst_d.data_ptr(),
+                            self.dst_off_d.data_ptr(), self.dst_cap_d.data_ptr(), self.out_len_d.data_ptr(), self.status_d.data_ptr(), self.n, st)
+
+    def verify(self):
+        """untimed: all blocks OK and (decode) bytes identical to the originals / (hash) values equal to the oracle's"""
+        torch, wl = self.torch, self.wl
+        assert int((self.status_d != 0).sum()) == 0, "kernel reported errors"
+        if self.opname == "hash":
+            d = wl["distinct"]
+            got = self.out_len_d[:d].cpu().numpy()
+            for i in range(0, d, max(1, d // 16)):
+                blk = wl["raw"][wl["raw_off"][i]:wl["raw_off"][i] + wl["raw_len"][i]]
+                assert int(got[i]) & 0xFFFFFFFFFFFFFFFF == self.orc.xxh64(blk.tobytes(), 0), "xxh64 mismatch"
+        elif self.opname == "decompress":
+            assert bool((self.out_len_d == self.raw_len_d).all())
+            end = int(self.raw_off_h[-1] + self.raw_len_h[-1])
+            assert torch.equal(self.dst_d[:end], self.raw_d[:end]), "decompressed batch differs from the original bytes"
+        else:
+            self.comp_bytes = int(self.out_len_d.sum())
+
+    def time(self, steps, warmup, barrier):
+        """warm-up + verification, then `steps` launches bracketed by barrier + synchronize; returns (total ms, per-launch ms list)"""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        self.verify()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        launches0 = self.eng.kernel_launches
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for a, b in evs:
+            a.record(); self.step(); b.record()
+        t_end.record()
+        barrier()
+        self.timed_launches = self.eng.kernel_launches - launches0
+        return t_start.elapsed_time(t_end), [a.elapsed_time(b) for a, b in evs]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,7 +357,7 @@ def main():
     ap.add_argument("--block-kib", type=int, default=0, help="default 64 (lz4/snappy) or 128 (zstd)")
     ap.add_argument("--blocks", type=int, default=0, help="default: 4 GiB of uncompressed data per GPU")
     ap.add_argument("--ref-blocks", type=int, default=8192, help="bounded sample for the CPU arms")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extra", action="store_true", help="skip the short per-codec side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -307,93 +402,35 @@ def main():
     n = args.blocks
 
     # ---------------- workload (weak scaling: every rank owns a full batch) ----------------
-    wl = build_workload(args.codec, args.block_kib, n, orc, threads)
-
-    def to_dev_tiled(packed, off, ln):
-        reps, stride, stride_al, offs, lens = tile_index(off, ln, n)
-        one = torch.zeros(stride_al, dtype=torch.uint8, device=dev)
-        one[:stride] = torch.from_numpy(packed).to(dev)
-        buf = one.repeat(reps)
-        return buf, torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev), offs, lens
-
-    raw_d, raw_off_d, raw_len_d, raw_off_h, raw_len_h = to_dev_tiled(wl["raw"], wl["raw_off"], wl["raw_len"])
-    unc_bytes = int(raw_len_h.sum())
-    if args.op == "hash":
-        src_d, src_off_d, src_len_d, src_off_h, src_len_h = raw_d, raw_off_d, raw_len_d, raw_off_h, raw_len_h
-        dst_d = torch.zeros(16, dtype=torch.uint8, device=dev)
-        dst_off_d = torch.zeros(n, dtype=torch.int64, device=dev)
-        dst_cap_d = torch.zeros(n, dtype=torch.int64, device=dev)
-        comp_bytes = 0
-    elif args.op == "decompress":
-        src_d, src_off_d, src_len_d, src_off_h, src_len_h = to_dev_tiled(wl["comp"], wl["comp_off"], wl["comp_len"])
-        dst_d = torch.zeros_like(raw_d)
-        dst_off_d, dst_cap_d = raw_off_d, raw_len_d
-        comp_bytes = int(src_len_h.sum())
-    else:
-        src_d, src_off_d, src_len_d, src_off_h, src_len_h = raw_d, raw_off_d, raw_len_d, raw_off_h, raw_len_h
-        bound = int(getattr(acb.lib(), f"acc_{args.codec}_compress_bound")(int(raw_len_h.max())))
-        dst_d = torch.zeros(bound * n, dtype=torch.uint8, device=dev)
-        dst_off_d = torch.arange(n, dtype=torch.int64, device=dev) * bound
-        dst_cap_d = torch.full((n,), bound, dtype=torch.int64, device=dev)
-        comp_bytes = None
-    out_len_d = torch.zeros(n, dtype=torch.int64, device=dev)
-    status_d = torch.zeros(n, dtype=torch.int32, device=dev)
-
     # all device work of the benchmark runs on one explicit stream; its handle is what the C ABI gets
-    # (handle 0 would mean "the context's own stream" to acc_batch, which torch events cannot see)
     bench_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(bench_stream)
-
-    def step():
-        st = torch.cuda.current_stream().cuda_stream
-        assert st != 0
-        eng.run_device(op, src_d.data_ptr(), src_off_d.data_ptr(), src_len_d.data_ptr(), dst_d.data_ptr(), dst_off_d.data_ptr(),
-                       dst_cap_d.data_ptr(), out_len_d.data_ptr(), status_d.data_ptr(), n, st)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    # verification (untimed): all blocks OK and bytes identical to the originals
-    assert int((status_d != 0).sum()) == 0, "kernel reported errors"
-    if args.op == "hash":
-        d = wl["distinct"]
-        got = out_len_d[:d].cpu().numpy()
-        for i in range(0, d, max(1, d // 16)):
-            blk = wl["raw"][wl["raw_off"][i]:wl["raw_off"][i] + wl["raw_len"][i]]
-            assert int(got[i]) & 0xFFFFFFFFFFFFFFFF == orc.xxh64(blk.tobytes(), 0), "xxh64 mismatch"
-        comp_bytes = 0
-    elif args.op == "decompress":
-        assert bool((out_len_d == raw_len_d).all())
-        end = int(raw_off_h[-1] + raw_len_h[-1])
-        assert torch.equal(dst_d[:end], raw_d[:end]), "decompressed batch differs from the original bytes"
-    else:
-        comp_bytes = int(out_len_d.sum())
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    launches0 = eng.kernel_launches
+    run = DeviceRun(acb, eng, orc, dev, args.codec, args.op, args.block_kib, n, threads)
+    wl = run.wl
+    unc_bytes = run.unc_bytes
+    src_d, dst_d, out_len_d = run.src_d, run.dst_d, run.out_len_d
+    src_off_h, src_len_h, dst_off_d, dst_cap_d = run.src_off_h, run.src_len_h, run.dst_off_d, run.dst_cap_d
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for a, b in evs:
-        a.record(); step(); b.record()
-    t_end.record()
-    barrier()
+    total_ms, kernel_ms = run.time(args.steps, args.warmup, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = t_start.elapsed_time(t_end)
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    launches = eng.kernel_launches - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t[0])
+    launches = run.timed_launches
+    comp_bytes = run.comp_bytes
+    total_ms = max_over_ranks(total_ms)
     value = world * args.steps * unc_bytes / (total_ms / 1e3) / GiB
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) ----------------
@@ -442,12 +479,69 @@ def main():
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:200]}
 
+    # ---------------- single-block calls: the Java-shaped entry points (acc_<codec>_<op>: pageable host memory, one block) ----------------
+    single = None
+    if rank == 0 and not args.profile and args.op != "hash":
+        try:
+            L = acb.lib()
+            i0 = wl["distinct"] // 2
+            blk = np.ascontiguousarray(wl["raw"][wl["raw_off"][i0]:wl["raw_off"][i0] + wl["raw_len"][i0]])
+            stream = np.ascontiguousarray(wl["comp"][wl["comp_off"][i0]:wl["comp_off"][i0] + wl["comp_len"][i0]])
+            cbound = int(getattr(L, f"acc_{args.codec}_compress_bound")(blk.size))
+            cbuf, dbuf = np.zeros(cbound, dtype=np.uint8), np.zeros(blk.size, dtype=np.uint8)
+            fc, fd = getattr(L, f"acc_{args.codec}_compress"), getattr(L, f"acc_{args.codec}_decompress")
+            h = eng._ctx.handle
+
+            def lat(f, a, alen, b, blen, reps=200):
+                ts = []
+                for _ in range(reps + 20):
+                    t0 = time.perf_counter()
+                    r = f(h, a.ctypes.data, alen, b.ctypes.data, blen)
+                    ts.append(time.perf_counter() - t0)
+                    assert r > 0
+                return float(np.median(ts[20:]) * 1e6)
+            d_us = lat(fd, stream, stream.size, dbuf, blk.size)
+            assert np.array_equal(dbuf, blk)
+            c_us = lat(fc, blk, blk.size, cbuf, cbound)
+            single = {"block_bytes": int(blk.size), "decompress_us": d_us, "compress_us": c_us, "calls": 200,
+                      "path": f"acc_{args.codec}_decompress / _compress: pinned staging, upload, kernel, download, one stream sync per call (median)"}
+        except Exception as ex:  # noqa: BLE001
+            single = {"error": repr(ex)[:160]}
+
+    # ---------------- extras: the other codec-directions of BASELINE.json configs[2..3] at this N ----------------
+    # 1 GiB of uncompressed data per GPU each (Snappy / LZ4 at 64 KiB, Zstandard at 128 KiB), device-resident, same timing
+    # rules as the headline (3 warm-ups, CUDA events, barrier on both sides, max over ranks); every run verifies itself.
+    peak, peak_src = hbm_peak()
+    extras = None
+    if not args.no_extra and not args.profile and args.op != "hash":
+        del run, src_d, dst_d, out_len_d, dst_off_d, dst_cap_d
+        torch.cuda.empty_cache()
+        extras = {}
+        for codec, opname, kib in (("lz4", "decompress", 64), ("lz4", "compress", 64), ("snappy", "decompress", 64), ("snappy", "compress", 64),
+                                   ("zstd", "decompress", 128), ("zstd", "compress", 128)):
+            if (codec, opname, kib) == (args.codec, args.op, args.block_kib):
+                continue
+            try:
+                nb = (1 << 20) // kib
+                r = DeviceRun(acb, eng, orc, dev, codec, opname, kib, nb, threads)
+                x_steps = 5
+                tms, kms = r.time(x_steps, 3, barrier)
+                tms = max_over_ranks(tms)
+                extras[f"{codec}_{opname}"] = {
+                    "value": world * x_steps * r.unc_bytes / (tms / 1e3) / GiB, "unit": "GiB/s", "block_kib": kib, "blocks_per_gpu": nb,
+                    "steps": x_steps, "warmup": 3, "ratio": (r.comp_bytes / r.unc_bytes) if r.comp_bytes else None,
+                    "roofline_frac": r.unc_bytes / (float(np.mean(kms)) / 1e3) / 1e9 / peak,
+                    "frac_min_traffic": (r.unc_bytes + (r.comp_bytes or 0)) / (float(np.mean(kms)) / 1e3) / 1e9 / peak}
+                del r
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001 -- an extra must never cost the headline line
+                extras[f"{codec}_{opname}"] = {"value": None, "error": repr(ex)[:160]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = hbm_peak()
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = unc_bytes / (avg_kernel_ms / 1e3) / 1e9
     traffic = None
@@ -476,12 +570,12 @@ def main():
         "metric": f"{args.codec}_{args.op}_uncompressed_GiB_per_s", "value": value, "unit": "GiB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": f"synthetic batch: {wl['label']}, tiled",
-        "config": {"workload": f"{args.codec} block {args.op}, {args.block_kib} KiB blocks x {n} batch per GPU (BASELINE.json configs[1] shape)",
+        "config": {"workload": f"{args.codec} block {args.op}, {args.block_kib} KiB blocks x {n} batch per GPU" + (" (BASELINE.json configs[1])" if (args.codec, args.op, args.block_kib, n) == ("lz4", "decompress", 64, 65536) else ""),
                    "distinct_blocks": wl["distinct"], "uncompressed_bytes_per_gpu": unc_bytes, "compressed_bytes_per_gpu": comp_bytes,
                    "ratio": (comp_bytes / unc_bytes) if comp_bytes else None, "parallelism": f"independent blocks, batch per GPU x{world}, no collective",
                    "l2": "inputs+outputs (>= 4 GiB per step) far exceed the 126 MB L2; no flush needed",
                    "input_streams": "reference algorithm (oracle port of Lz4RawCompressor etc.), prepared untimed"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "single_block": single, "extras": extras, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

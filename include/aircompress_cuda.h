@@ -59,7 +59,6 @@ extern "C" {
 /* ---- flags for batch calls --------------------------------------------------------------------- */
 #define ACC_F_DEVICE_POINTERS 1  /* src/dst bases and all index/result arrays are device pointers; the call is
                                     asynchronous on `stream` (no host<->device copies, no synchronisation) */
-#define ACC_F_NO_SYNC         2  /* host-pointer mode only: reserved */
 
 typedef struct acc_ctx acc_ctx;
 
@@ -76,6 +75,19 @@ const char *acc_code_name(int32_t code);
 const char *acc_reason_text(int32_t reason);     /* the reference's exception message for that reason */
 int32_t  acc_sm_count(acc_ctx *ctx);
 int64_t  acc_kernel_launches(acc_ctx *ctx);      /* kernels launched through this ctx so far (bench.py gpu_launches) */
+
+/* per-context counters since acc_init (the reference has no tracing; this is the hook a caller can poll).
+ * Copies min(words, ACC_STATS_WORDS) int64 values into out[] and returns that count. */
+#define ACC_STAT_BATCHES        0   /* kernel batches enqueued (host- and device-pointer calls; pipelined runs count each) */
+#define ACC_STAT_BLOCKS         1   /* blocks in those batches */
+#define ACC_STAT_LAUNCHES       2   /* kernel launches */
+#define ACC_STAT_HOST_CALLS     3   /* host-pointer calls (single-block calls included) */
+#define ACC_STAT_H2D_BYTES      4   /* bytes uploaded by host-pointer calls (payload + index arrays) */
+#define ACC_STAT_D2H_BYTES      5   /* bytes downloaded by host-pointer calls (output windows + result arrays) */
+#define ACC_STAT_LAST_CALL_US   6   /* wall time of the last host-pointer call: staging, upload, kernels, download, sync */
+#define ACC_STAT_TOTAL_CALL_US  7   /* sum of the above over all host-pointer calls */
+#define ACC_STATS_WORDS         8
+int32_t  acc_get_stats(acc_ctx *ctx, int64_t *out, int32_t words);
 
 /* ---- bounds: replace LZ4_compressBound (lz4/Lz4Native.java:31), snappy_max_compressed_length
  *      (snappy/SnappyNative.java:70), ZSTD_compressBound (zstd/ZstdNative.java:29).  Values follow the
@@ -125,6 +137,11 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
  * stream; pass 1 (cudaStreamLegacy) or 2 (cudaStreamPerThread) to target CUDA's default streams);
  * with ACC_F_DEVICE_POINTERS the work is only enqueued (at most 100 batches may be in flight per context:
  * every launch takes one or two of the context's 256 work-stealing counters, which are reused round-robin).
+ * Batches of ONE context are ordered: a batch enqueued on a different stream than the previous one first waits for
+ * it (the context's scratch and counters are shared), so use one context per concurrent stream of work.
+ * Device buffers: kernels read whole aligned 4-byte words, i.e. up to 3 bytes in front of / behind a block's
+ * [src_off, src_off + src_len) range -- never beyond the 4-byte-aligned extent of src_base's allocation (cudaMalloc
+ * sizes are multiples of 256 bytes), so pad a sub-allocated source buffer to a multiple of 4 bytes.
  * Without it the library copies host->device,
  * runs, copies results back and synchronises before returning; large batches are cut into runs of consecutive
  * blocks whose upload, kernel and download overlap (see acc_set_tuning key 3).
@@ -148,8 +165,7 @@ int32_t acc_zstd_decompress_batch(acc_ctx *, const void *, const int64_t *, cons
 int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, int64_t *, int64_t, int32_t, int64_t);
 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
- * key 0: resident CTAs per SM for the warp-per-block decode kernels; key 1: LZ4 decoder (1 = warp per block,
- * 2 = thread per block, 3 = shared-memory window); key 2: CTA count of the thread-per-block decoder;
+ * key 0: resident CTAs per SM for the warp-per-block decode kernels;
  * key 3: host-pointer batches, 1 = never split, k > 1 = split into k overlapped upload/kernel/download runs
  * (default: automatic, up to 16 runs of >= 4096 blocks and >= 32 MiB each); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);

@@ -1,31 +1,34 @@
-"""Joins an ncu SASS source page (per-instruction counts) with nvdisasm -g line info of the same build:
-python tools/ncu_lines.py <sass.csv from `ncu -i rep --page source --csv --print-source sass`> <nvdisasm -g -c output> [kernel-substr]
-Prints instructions executed and stall samples per source line, heaviest first."""
-import csv, re, sys, collections
-rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]; data = rows[2:]
-ie = hdr.index('Instructions Executed'); sm = hdr.index('# Samples'); te = hdr.index('Thread Instructions Executed')
-prof = [(r[1].strip(), int(r[ie]), int(r[sm]), int(r[te])) for r in data]
-# disassembly: sequence of (file,line) per instruction for the wanted function
-pat = sys.argv[3] if len(sys.argv) > 3 else None
-cur = None; infn = False; lines = []
-for l in open(sys.argv[2]):
-    m = re.match(r'\s*\.section\s+\.text\.(\S+),', l)
-    if m:
-        infn = pat is None or pat in m.group(1); continue
-    if not infn: continue
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
-    m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
-    if m: lines.append((cur, m.group(2).strip()))
-print('profile instrs', len(prof), 'disasm instrs', len(lines), file=sys.stderr)
-n = min(len(prof), len(lines))
-mism = sum(1 for i in range(n) if prof[i][0].split()[0:1] != lines[i][1].replace('{','').split()[0:1])
-print('opcode mismatches', mism, file=sys.stderr)
-agg = collections.defaultdict(lambda: [0, 0, 0, 0])
-for i in range(n):
-    a = agg[lines[i][0]]; a[0] += prof[i][1]; a[1] += prof[i][2]; a[2] += 1; a[3] += prof[i][3]
-tot = sum(a[0] for a in agg.values()); tots = sum(a[1] for a in agg.values())
-print(f'total instr {tot/1e9:.2f}G samples {tots}')
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[4]) if len(sys.argv) > 4 else 45]:
-    print(f'{str(k):40s} instr% {100*a[0]/tot:5.1f}  samples% {100*a[1]/tots:5.1f}  sass {a[2]:4d}  lanes {a[3]/max(1,a[0]):4.1f}')
+"""Per-source-line view of an ncu capture: joins the SASS page of a report (ncu --page source --csv) with the line table of
+the cubin (nvdisasm -g), in instruction order.  usage: python tools/ncu_lines.py <report.ncu-rep> <cubin> <kernel-substring> [top]"""
+import csv, io, re, subprocess, sys
+from collections import defaultdict
+
+def main(rep, cubin, kname, top=40):
+    sass = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout.splitlines()
+    lines, cur, inside = [], None, False
+    for ln in sass:
+        if ln.startswith('.text.') or ln.strip().startswith('.section'):
+            inside = kname in ln and '.text.' in ln
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = (m.group(1).split('/')[-1], int(m.group(2)))
+            continue
+        if inside and re.match(r'\s+/\*[0-9a-f]{4,}\*/', ln):
+            lines.append(cur)
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, data = rows[1], rows[2:]
+    ia, isamp = hdr.index('Instructions Executed'), hdr.index('# Samples')
+    if len(data) != len(lines):
+        print('warning: %d SASS rows in the report, %d in the cubin' % (len(data), len(lines)))
+    agg = defaultdict(lambda: [0, 0])
+    for r, l in zip(data, lines):
+        agg[l][0] += int(r[ia]); agg[l][1] += int(r[isamp])
+    ti = sum(v[0] for v in agg.values()) or 1; ts = sum(v[1] for v in agg.values()) or 1
+    print('total warp instructions %d, samples %d' % (ti, ts))
+    for l, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print('%-28s inst %5.2f%%  samples %5.2f%%' % ('%s:%d' % l if l else '?', 100.0 * v[0] / ti, 100.0 * v[1] / ts))
+    return agg
+
+if __name__ == '__main__':
+    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
