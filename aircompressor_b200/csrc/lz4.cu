@@ -46,12 +46,15 @@ __device__ __forceinline__ uint32_t lz4_hash5(uint64_t v)
     return (uint32_t) ((v * 889523592379ULL) >> 28) & (kLz4Table - 1);
 }
 
-// lanes cooperatively write the run-length header [token + extension bytes]; returns new position
-__device__ __forceinline__ int64_t lz4_emit_literal_run(uint8_t *out, int64_t op, const uint8_t *lit, int64_t ll, uint8_t **token_ptr, int lane)
+// lanes cooperatively write a sequence's token (literal length nibble + match code nibble, known together: the token is
+// written once, never read back), the literal-length extension bytes and the literals; returns the new position.
+// mcode < 0: last literals (no match part).
+__device__ __forceinline__ int64_t lz4_emit_literal_run(uint8_t *out, int64_t op, const uint8_t *lit, int64_t ll, int64_t mcode, int lane)
 {
+    const uint32_t ml_nibble = mcode < 0 ? 0u : (mcode >= 15 ? 15u : (uint32_t) mcode);
     uint8_t *token = out + op++;
     if (ll >= 15) {
-        if (lane == 0) *token = 0xF0;
+        if (lane == 0) *token = (uint8_t) (0xF0u | ml_nibble);
         int64_t rem = ll - 15;
         int64_t n255 = rem / 255;
         for (int64_t i = lane; i < n255; i += 32) out[op + i] = 255;
@@ -59,10 +62,9 @@ __device__ __forceinline__ int64_t lz4_emit_literal_run(uint8_t *out, int64_t op
         op += n255 + 1;
     }
     else {
-        if (lane == 0) *token = (uint8_t) (ll << 4);
+        if (lane == 0) *token = (uint8_t) ((uint32_t) (ll << 4) | ml_nibble);
     }
     warp_copy(out + op, lit, ll, lane);
-    *token_ptr = token;
     return op + ll;
 }
 
@@ -113,25 +115,27 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
             while (pos <= match_find_limit) {
                 // ---- probe 32 positions ----
                 const int64_t p = pos + lane;
+                const bool live = p <= match_find_limit;
                 bool hit = false;
                 int32_t cand = -1;
-                if (p <= match_find_limit) {
-                    uint64_t v = ld_u64_unaligned(in + p);
-                    uint32_t h = lz4_hash5(v);
-                    const TableT tv = table[h];
+                uint32_t slot = 0xFFFFFFFFu - (uint32_t) lane;          // idle lanes: distinct dummies for the insert below
+                if (live) {
+                    const uint64_t v = ld_u64_unaligned(in + p);
+                    slot = lz4_hash5(v);
+                    const TableT tv = table[slot];
                     cand = tv == kEmpty ? -1 : (int32_t) tv;
                     if (cand >= 0 && cand < p && p - cand <= 65535 && ld_u32_unaligned(in + cand) == (uint32_t) v) hit = true;
                 }
                 __syncwarp();
                 // Insert after the lookups (lanes see the table as of the batch start), and only positions up to
                 // the first match: a position behind the match end would otherwise be looked up again by the next
-                // batch and find itself instead of its older candidate.
+                // batch and find itself instead of its older candidate.  (Two lanes of one step can hash to
+                // the same slot; which store lands last is the hardware's choice -- in practice the highest lane, and
+                // tests/test_gpu_determinism.py pins that the output does not vary -- a __match_any_sync arbitration made
+                // the choice explicit but cost 15 % of the kernel.)
                 unsigned hits = __ballot_sync(kFull, hit);
                 const int first_hit = hits ? __ffs(hits) - 1 : 31;
-                if (p <= match_find_limit && lane <= first_hit) {
-                    uint64_t v = ld_u64_unaligned(in + p);
-                    table[lz4_hash5(v)] = (TableT) p;
-                }
+                if (live && lane <= first_hit) table[slot] = (TableT) p;
                 if (hits == 0) {
                     pos += 32;
                     continue;
@@ -139,8 +143,15 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                 const int first = __ffs(hits) - 1;
                 int64_t mpos = pos + first;                              // match start in input
                 int64_t ref = __shfl_sync(kFull, cand, first);           // candidate position
-                // catch up backwards (Lz4RawCompressor.java:141-144)
-                while (mpos > anchor && ref > 0 && in[mpos - 1] == in[ref - 1]) { --mpos; --ref; }
+                // catch up backwards (Lz4RawCompressor.java:141-144), 32 bytes per ballot instead of a chain of dependent byte loads
+                for (;;) {
+                    const int64_t room = (mpos - anchor) < ref ? (mpos - anchor) : ref;
+                    const bool eq1 = lane < room && in[mpos - 1 - lane] == in[ref - 1 - lane];
+                    const unsigned m = __ballot_sync(kFull, eq1);
+                    const int nb = m == kFull ? 32 : __ffs(~m) - 1;
+                    mpos -= nb; ref -= nb;
+                    if (nb < 32) break;
+                }
 
                 // ---- extend the match forwards, 32 bytes per ballot ----
                 int64_t mlen = kMinMatch;
@@ -153,16 +164,13 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                     break;
                 }
 
-                // ---- emit: literals [anchor, mpos), then the match ----
-                uint8_t *token;
-                op = lz4_emit_literal_run(out, op, in + anchor, mpos - anchor, &token, lane);
+                // ---- emit: token + literals [anchor, mpos), then offset and match-length extension ----
                 const uint32_t offset = (uint32_t) (mpos - ref);
-                int64_t mcode = mlen - kMinMatch;
-                __syncwarp();
+                const int64_t mcode = mlen - kMinMatch;
+                op = lz4_emit_literal_run(out, op, in + anchor, mpos - anchor, mcode, lane);
                 if (lane == 0) {
                     out[op] = (uint8_t) offset;
                     out[op + 1] = (uint8_t) (offset >> 8);
-                    if (mcode >= 15) *token |= 15; else *token |= (uint8_t) mcode;
                 }
                 op += 2;
                 if (mcode >= 15) {
@@ -178,8 +186,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
             }
         }
         // ---- last literals ----
-        uint8_t *token;
-        op = lz4_emit_literal_run(out, op, in + anchor, in_len - anchor, &token, lane);
+        op = lz4_emit_literal_run(out, op, in + anchor, in_len - anchor, -1, lane);
         if (lane == 0) { b.out_len[idx] = op; b.status[idx] = 0; }
         __syncwarp();
     }

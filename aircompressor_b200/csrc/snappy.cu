@@ -133,19 +133,22 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
             int64_t pos = 0;
             while (pos <= fast_limit) {
                 const int64_t p = pos + lane;
+                const bool live = p <= fast_limit;
                 bool hit = false;
                 uint32_t cand = 0xffff;
-                uint32_t cur = 0;
-                if (p <= fast_limit) {
-                    cur = ld_u32_unaligned(base + p);
-                    cand = table[snappy_hash(cur)];
+                uint32_t slot = 0xFFFFFFFFu - (uint32_t) lane;          // idle lanes: distinct dummies for the insert below
+                if (live) {
+                    const uint32_t cur = ld_u32_unaligned(base + p);
+                    slot = snappy_hash(cur);
+                    cand = table[slot];
                     if (cand != 0xffff && cand < p && ld_u32_unaligned(base + cand) == cur) hit = true;
                 }
                 __syncwarp();
-                // insert only up to the first match (see lz4.cu); position 65535 cannot be stored (0xffff = empty)
+                // insert only up to the first match (see lz4.cu); position 65535
+                // cannot be stored (0xffff = empty)
                 unsigned hits = __ballot_sync(kFull, hit);
                 const int first_hit = hits ? __ffs(hits) - 1 : 31;
-                if (p <= fast_limit && p < 0xffff && lane <= first_hit) table[snappy_hash(cur)] = (uint16_t) p;
+                if (live && p < 0xffff && lane <= first_hit) table[slot] = (uint16_t) p;
                 if (hits == 0) { pos += 32; continue; }
                 const int first = __ffs(hits) - 1;
                 const int64_t mpos = pos + first;

@@ -146,25 +146,31 @@ __device__ __forceinline__ int fse_begin(const uint16_t *next_state, const int32
     return next_state[base + dfs[symbol]];
 }
 
-// HuffmanCompressionTable.buildTree + setMaxHeight (zstd/HuffmanCompressionTable.java:105-190, :294-390), single thread.
-// Produces code lengths in hbits[] and canonical values in hcode[]; returns the maximum code length used.
-__device__ int huf_build(EncSmem &sm, int max_symbol, int max_bits)
+// The leaf order of HuffmanCompressionTable.buildTree (:105-130: insertion sort, descending by count, equal counts in symbol
+// order) as a rank sort over all 256 threads: thread s counts the symbols that come before symbol s.  Also clears the
+// node table.  Call with all kThreads threads, __syncthreads() afterwards.
+__device__ __forceinline__ void huf_sort_leaves(EncSmem &sm)
 {
     NodeTable &nt = sm.u.nt;
-    for (int i = 0; i < 512; i++) { nt.count[i] = 0; nt.parents[i] = 0; nt.symbols[i] = 0; nt.nbits[i] = 0; }
-    int current = 0;
-    for (int symbol = 0; symbol <= max_symbol; symbol++) {
-        int count = (int) sm.hist[symbol];
-        int position = current;
-        while (position > 0 && count > nt.count[position - 1]) {   // plain insertion sort, descending by count
-            nt.count[position] = nt.count[position - 1];
-            nt.symbols[position] = nt.symbols[position - 1];
-            position--;
-        }
-        nt.count[position] = count;
-        nt.symbols[position] = (int16_t) symbol;
-        current++;
+    const int t = threadIdx.x;
+    for (int i = t; i < 512; i += kThreads) { nt.count[i] = 0; nt.parents[i] = 0; nt.symbols[i] = 0; nt.nbits[i] = 0; }
+    __syncthreads();
+    if (t < 256) {
+        const uint32_t mine = sm.hist[t];
+        int rank = 0;
+        for (int s = 0; s < 256; s++) { const uint32_t c = sm.hist[s]; rank += (c > mine) || (c == mine && s < t); }
+        nt.count[rank] = (int32_t) mine;
+        nt.symbols[rank] = (int16_t) t;
     }
+}
+
+// HuffmanCompressionTable.buildTree + setMaxHeight (zstd/HuffmanCompressionTable.java:105-190, :294-390), single thread, on
+// the leaves huf_sort_leaves ordered.  Produces code lengths in hbits[] and canonical values in hcode[]; returns the
+// maximum code length used.
+__device__ int huf_build(EncSmem &sm, int max_symbol, int max_bits)
+{
+    NodeTable &nt = sm.u.nt;   // leaves sorted by huf_sort_leaves, the rest zeroed
+    int current = 0;
     int last_non_zero = max_symbol;
     while (nt.count[last_non_zero] == 0) last_non_zero--;
     const int non_leaf_start = 256;
@@ -431,8 +437,7 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                             const int p = base + lane;
                             uint32_t h = 0, slot = 0xFFFFFFFFu - (uint32_t) lane;   // idle lanes: distinct dummies
                             if (p < lim) { h = zenc_long_hash(ld_u64_unaligned(blk + p)); slot = h & ((1u << kLongLog) - 1); }
-                            const unsigned peers = __match_any_sync(kFull, slot);   // equal slots in one step: the highest position wins
-                            if (p < lim && lane == 31 - __clz(peers)) fin[slot] = (uint16_t) ((uint32_t) (p - qs) | ((h >> kLongLog) << 14));
+                            if (p < lim) fin[slot] = (uint16_t) ((uint32_t) (p - qs) | ((h >> kLongLog) << 14));   // equal slots in one step: see lz4.cu
                             __syncwarp();
                         }
                     }
@@ -486,11 +491,8 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         }
                         const unsigned hits = __ballot_sync(kFull, cand >= 0);
                         const int first_hit = hits ? __ffs(hits) - 1 : 31;
-                        // Insert after the lookups, and only positions up to the first match (see lz4.cu); of equal slots in one
-                        // step the highest position wins, so the table -- and with it the output -- does not depend on timing.
-                        const bool ins = live && lane <= first_hit;
-                        const unsigned peers = __match_any_sync(kFull, ins ? sslot : 0xFFFFFFFFu - (uint32_t) lane);
-                        if (ins && lane == 31 - __clz(peers)) inc[sslot] = (uint16_t) (p - qs);
+                        // insert after the lookups, and only positions up to the first match (see lz4.cu)
+                        if (live && lane <= first_hit) inc[sslot] = (uint16_t) (p - qs);
                         __syncwarp();
                         if (hits == 0) { pos += 32; continue; }
                         int mpos = pos + first_hit;
@@ -542,46 +544,10 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                     for (int k = 1; k < kNQ; k++) w += (i >= sm.qbase[k]);
                     return seqs[(int64_t) w * kMaxSeqQ + (i - sm.qbase[w])];
                 };
-                auto seq_at = [&](int i) -> uint64_t { return seqc[i]; };   // valid after the repeated-offset pass
-                // ================= 2b. repeated offsets (RFC 8878 3.1.1.5, RepeatedOffsets.java:16-49) =================
-                // One thread walks the list with the decoder's history and turns every offset into its offset VALUE: 1..3 for a
-                // repeat code, offset + 3 otherwise.  The list passes through shared memory in tiles (the match tables are free now)
-                // and lands in one contiguous array.
-                {
-                    constexpr int kTile = (int) (sizeof(sm.u.rep) / 4);
-                    if (tid == 0) { sm.v[V_REPT1] = sm.v[V_REP1]; sm.v[V_REPT2] = sm.v[V_REP2]; sm.v[V_REPT3] = sm.v[V_REP3]; }
-                    for (int t0 = 0; t0 < nseq; t0 += kTile) {
-                        const int tn = min(kTile, nseq - t0);
-                        __syncthreads();
-                        for (int i = tid; i < tn; i += kThreads) { const uint64_t sq = seq_raw(t0 + i); sm.u.rep[i] = seq_off(sq) | (seq_ll(sq) ? 0x80000000u : 0u); }
-                        __syncthreads();
-                        if (tid == 0) {
-                            int r1 = sm.v[V_REPT1], r2 = sm.v[V_REPT2], r3 = sm.v[V_REPT3];
-                            for (int i = 0; i < tn; i++) {
-                                const uint32_t e = sm.u.rep[i];
-                                const int o = (int) (e & 0x7FFFFFFFu);
-                                uint32_t val = (uint32_t) o + 3;
-                                if (e >> 31) {                      // literals in front of the match
-                                    if (o == r1) val = 1;
-                                    else if (o == r2) { val = 2; r2 = r1; r1 = o; }
-                                    else { if (o == r3) val = 3; r3 = r2; r2 = r1; r1 = o; }
-                                }
-                                else {                              // no literals: the codes mean rep2, rep3, rep1 - 1
-                                    if (o == r2) { val = 1; r2 = r1; r1 = o; }
-                                    else { if (o == r3) val = 2; else if (o == r1 - 1) val = 3; r3 = r2; r2 = r1; r1 = o; }
-                                }
-                                sm.u.rep[i] = val;
-                            }
-                            sm.v[V_REPT1] = r1; sm.v[V_REPT2] = r2; sm.v[V_REPT3] = r3;
-                        }
-                        __syncthreads();
-                        for (int i = tid; i < tn; i += kThreads) {
-                            const uint64_t sq = seq_raw(t0 + i);
-                            seqc[t0 + i] = pack_seq(seq_ll(sq), seq_ml(sq), sm.u.rep[i]);   // the compact list every later stage reads
-                        }
-                    }
-                    __syncthreads();
-                }
+                auto seq_at = [&](int i) -> uint64_t { return seqc[i]; };   // the concatenated list (offsets become offset values in step 3b)
+                // the eight lists as one contiguous array: every later stage indexes it directly
+                for (int i = tid; i < nseq; i += kThreads) seqc[i] = seq_raw(i);
+                __syncthreads();
                 const int chunk = (nseq + kThreads - 1) / kThreads;
                 const int c0 = min(tid * chunk, nseq), c1 = min(c0 + chunk, nseq);
                 int my_ll = 0, my_all = 0;
@@ -601,6 +567,48 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                 __syncthreads();
 
                 // ================= 3. literals section planning (ZstdFrameCompressor.encodeLiterals :262-378) =================
+                huf_sort_leaves(sm);
+                __syncthreads();
+                if (warp == kNQ - 1) {
+                    // ================= 3b. repeated offsets (RFC 8878 3.1.1.5, RepeatedOffsets.java:16-49), concurrently with 3 =====
+                    // Lane 0 walks the list with the decoder's history and turns every offset into its offset VALUE: 1..3 for a
+                    // repeat code, offset + 3 otherwise.  The list passes through shared memory in tiles (behind the Huffman node
+                    // table thread 0 is using meanwhile).
+                    constexpr int kTileAt = 2048;                                   // words; sizeof(NodeTable) < 8 KiB
+                    constexpr int kTile = (int) (sizeof(sm.u.rep) / 4) - kTileAt;
+                    static_assert(sizeof(NodeTable) <= kTileAt * 4, "node table overlaps the repeat-offset tile");
+                    uint32_t *tile = sm.u.rep + kTileAt;
+                    int r1 = sm.v[V_REP1], r2 = sm.v[V_REP2], r3 = sm.v[V_REP3];      // lane 0's copy is the one that counts
+                    for (int t0 = 0; t0 < nseq; t0 += kTile) {
+                        const int tn = min(kTile, nseq - t0);
+                        for (int i = lane; i < tn; i += 32) { const uint64_t sq = seqc[t0 + i]; tile[i] = seq_off(sq) | (seq_ll(sq) ? 0x80000000u : 0u); }
+                        __syncwarp();
+                        if (lane == 0) {
+                            for (int i = 0; i < tn; i++) {
+                                const uint32_t e = tile[i];
+                                const int o = (int) (e & 0x7FFFFFFFu);
+                                uint32_t val = (uint32_t) o + 3;
+                                if (e >> 31) {                      // literals in front of the match
+                                    if (o == r1) val = 1;
+                                    else if (o == r2) { val = 2; r2 = r1; r1 = o; }
+                                    else { if (o == r3) val = 3; r3 = r2; r2 = r1; r1 = o; }
+                                }
+                                else {                              // no literals: the codes mean rep2, rep3, rep1 - 1
+                                    if (o == r2) { val = 1; r2 = r1; r1 = o; }
+                                    else { if (o == r3) val = 2; else if (o == r1 - 1) val = 3; r3 = r2; r2 = r1; r1 = o; }
+                                }
+                                tile[i] = val;
+                            }
+                        }
+                        __syncwarp();
+                        for (int i = lane; i < tn; i += 32) {
+                            const uint64_t sq = seqc[t0 + i];
+                            seqc[t0 + i] = pack_seq(seq_ll(sq), seq_ml(sq), tile[i]);
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) { sm.v[V_REPT1] = r1; sm.v[V_REPT2] = r2; sm.v[V_REPT3] = r3; }
+                }
                 if (tid == 0) {
                     int mode = 0;   // 0 raw, 1 rle, 2 huffman
                     int max_symbol = 255, largest = 0, hbits = 0, table_bytes = 0;
