@@ -558,6 +558,23 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
             remaining = __shfl_sync(kFull, remaining, 0);
             stop = __shfl_sync(kFull, (int) stop, 0) != 0;
             __syncwarp();
+            // Every sequence of the batch knows where its literals and its match source lie (prefix sums over the batch), so
+            // lane s asks for the lines of sequence s now: the copies below then find them in L1 instead of paying one
+            // L2 round trip per sequence (stores do not allocate in L1, and the literal buffer is global scratch).
+            {
+                int32_t a = lane < produced ? sm.seq_ll[lane] : 0, t = lane < produced ? sm.seq_ll[lane] + sm.seq_ml[lane] : 0;
+                const int32_t my_ll = a;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int32_t ua = __shfl_up_sync(kFull, a, o), ut = __shfl_up_sync(kFull, t, o);
+                    if (lane >= o) { a += ua; t += ut; }
+                }
+                if (lane < produced) {
+                    const int64_t lp = lit_pos + (a - my_ll);                       // literal position of sequence `lane`
+                    const int64_t ms = output + (t - sm.seq_ml[lane]) - sm.seq_of[lane];   // its match source
+                    if (lit.rle < 0 && my_ll > 0 && lp < lit.size) asm volatile("prefetch.global.L1 [%0];" :: "l"(lit.ptr + lp));
+                    if (ms >= 0 && ms < output) asm volatile("prefetch.global.L1 [%0];" :: "l"(out + ms));
+                }
+            }
             // execute (all lanes, in order)
             for (int s = 0; s < produced; s++) {
                 const int64_t lit_length = sm.seq_ll[s], match_length = sm.seq_ml[s];
@@ -568,9 +585,19 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
                 const int64_t lit_end = lit_pos + lit_length;
                 ZCHECK(lit_end <= lit.size, input, R_CORRUPTED);
                 ZCHECK(lit_out_limit - offset >= 0, input, R_CORRUPTED);
-                copy_literals(out + output, lit, lit_pos, lit_length, lane);
-                __syncwarp();
-                warp_match_copy(out + lit_out_limit, offset, match_length, lane);
+                const int64_t total = lit_length + match_length;
+                if (total <= 32 && offset >= total && lit.rle < 0) {
+                    // the whole sequence in one step: a lane's byte is a literal or a match byte in front of this sequence
+                    if (lane < total) {
+                        const uint8_t *src = lane < lit_length ? lit.ptr + (lit_pos + lane) : out + (output + lane - offset);
+                        out[output + lane] = *src;
+                    }
+                }
+                else {
+                    copy_literals(out + output, lit, lit_pos, lit_length, lane);
+                    __syncwarp();
+                    warp_match_copy(out + lit_out_limit, offset, match_length, lane);
+                }
                 __syncwarp();
                 output = match_out_limit;
                 lit_pos = lit_end;
