@@ -6,6 +6,7 @@ this package is the host-side mirror of the reference interface used by tests an
 """
 from ._native import (F_DEVICE_POINTERS, OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS,
                       OP_XXH64, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, NativeLibraryMissing, lib)
+from .multi import MultiDeviceEngine
 from .api import (BatchEngine, Compressor, Decompressor, IllegalArgumentException, Lz4CudaCompressor, Lz4CudaDecompressor,
                   MalformedInputException, SnappyCudaCompressor, SnappyCudaDecompressor, XxHash64CudaHasher,
                   ZstdCudaCompressor, ZstdCudaDecompressor)

@@ -44,6 +44,8 @@ def lib():
         "acc_last_error": (i32, [vp, pi64]),
         "acc_code_name": (C.c_char_p, [i32]),
         "acc_reason_text": (C.c_char_p, [i32]),
+        "acc_device_numa_node": (i32, [i32]),
+        "acc_bind_host_thread": (i32, [i32]),
         "acc_sm_count": (i32, [vp]),
         "acc_kernel_launches": (i64, [vp]),
         "acc_set_tuning": (i32, [vp, i32, i32]),

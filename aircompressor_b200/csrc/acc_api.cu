@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#include <sched.h>
 #include "acc_device.cuh"
 
 struct acc_ctx {
@@ -115,6 +116,57 @@ int32_t acc_last_error(acc_ctx *c, int64_t *offset)
     if (!c) return ACC_STATUS(ACC_E_ARGUMENT, 0);
     if (offset) *offset = c->last_offset;
     return c->last_status;
+}
+
+// NUMA node of a CUDA device from sysfs (-1: unknown / not a NUMA machine)
+static int device_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int) sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char) (*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+int32_t acc_device_numa_node(int32_t device) { return device_numa_node(device); }
+
+// Restricts the CALLING THREAD to the CPUs of the device's NUMA node, so that what it allocates and pins afterwards
+// (first touch) and the staging copies it makes run next to the GPU's PCIe root.  Returns the node, or -1 when the
+// machine gives no answer (nothing is changed then).
+int32_t acc_bind_host_thread(int32_t device)
+{
+    const int node = device_numa_node(device);
+    if (node < 0) return -1;
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return -1;
+    cpu_set_t want, have;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(have), &have) != 0) return -1;
+    int any = 0;
+    for (char *p = list; *p;) {                              // "0-31,64-95"
+        char *e;
+        long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b2 = a;
+        if (*e == '-') { p = e + 1; b2 = strtol(p, &e, 10); }
+        for (long c = a; c <= b2 && c < CPU_SETSIZE; c++) if (CPU_ISSET((int) c, &have)) { CPU_SET((int) c, &want); any++; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    if (!any || sched_setaffinity(0, sizeof(want), &want) != 0) return -1;   // keep what the process was given if the node has none of it
+    return node;
 }
 
 int32_t acc_sm_count(acc_ctx *c) { return c ? c->sm_count : 0; }

@@ -362,6 +362,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--pipeline", type=int, default=0, help="host-pointer path: 0 auto, 1 single pass, k>1 overlapped runs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: ONE batch of --blocks blocks is split over the ranks (contiguous, byte-balanced: BASELINE.md s3 config 3 wording)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): no e2e, no cpu baseline, warm-up as given")
     args = ap.parse_args()
     if args.codec == "xxh64":
@@ -389,6 +391,9 @@ def main():
     import aircompressor_b200 as acb
     from oracle.pyoracle import Oracle  # input preparation + cpu_baseline leg only
 
+    # host side of this rank next to its GPU: CPU affinity first, so that everything pinned below is placed on that node
+    full_affinity = os.sched_getaffinity(0)
+    numa_node = -1 if args.no_numa_bind else int(acb.lib().acc_bind_host_thread(local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -400,6 +405,10 @@ def main():
         eng.set_tuning(0, args.ctas_per_sm)
     op = CODEC_OPS[(args.codec, args.op)]
     n = args.blocks
+    if args.scaling == "strong" and world > 1:
+        # one batch, contiguous split: the tiling makes every block of a residue class the same size, so an even split of the
+        # block range is the byte-balanced split of sharding.partition_by_bytes up to one tile
+        n = args.blocks // world + (1 if rank < args.blocks % world else 0)
 
     # ---------------- workload (weak scaling: every rank owns a full batch) ----------------
     # all device work of the benchmark runs on one explicit stream; its handle is what the C ABI gets
@@ -431,7 +440,14 @@ def main():
     launches = run.timed_launches
     comp_bytes = run.comp_bytes
     total_ms = max_over_ranks(total_ms)
-    value = world * args.steps * unc_bytes / (total_ms / 1e3) / GiB
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    job_unc_bytes = sum_over_ranks(unc_bytes)        # weak: world x the rank's batch; strong: the one batch
+    value = args.steps * job_unc_bytes / (total_ms / 1e3) / GiB
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) ----------------
     e2e = None
@@ -444,6 +460,21 @@ def main():
         hs, hd = h_src.numpy(), h_dst.numpy()
         so_h, sl_h = src_off_h, src_len_h
         do_h, dc_h = dst_off_d.cpu().numpy(), dst_cap_d.cpu().numpy()
+        # what the PCIe link of this GPU gives in each direction alone (pinned memory, one cudaMemcpyAsync), and the e2e value
+        # that bound allows when upload and download overlap perfectly: bytes / max(t_h2d, t_d2h)
+        def copy_gbps(dst_t, src_t, reps=3):
+            best = None
+            for _ in range(reps):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dst_t.copy_(src_t, non_blocking=True); b_.record(); torch.cuda.synchronize()
+                ms = a.elapsed_time(b_)
+                best = ms if best is None or ms < best else best
+            return src_t.numel() / (best / 1e3) / 1e9, best
+        h2d_gbps, h2d_ms = copy_gbps(src_d, h_src)
+        d2h_gbps, d2h_ms = copy_gbps(h_dst, dst_d)
+        link = {"h2d_GBps": h2d_gbps, "d2h_GBps": d2h_gbps, "numa_node": numa_node,
+                "overlap_bound_GiBps": unc_bytes / (max(h2d_ms, d2h_ms) / 1e3) / GiB}
+
         def timed_host_calls(pipeline):
             eng.set_tuning(3, pipeline)
             eng.run_host(op, hs, so_h, sl_h, hd, do_h, dc_h)  # warm staging allocations
@@ -471,10 +502,11 @@ def main():
             assert torch.equal(h_dst[:end], dst_d[:end].cpu()), "e2e output differs from the device-resident run"
         h2d = int(src_off_h[-1] + src_len_h[-1]) + 4 * 8 * n
         d2h = int(do_h[-1] + dc_h[-1]) + 12 * n
-        e2e = {"value": world * args.e2e_steps * unc_bytes / dt / GiB, "unit": "GiB/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": args.e2e_steps * job_unc_bytes / dt / GiB, "unit": "GiB/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "path": "acc_batch with pinned host buffers; upload, kernels and download of consecutive runs of blocks overlap on three streams, one sync per call",
-               "single_pass_value": (world * args.e2e_steps * unc_bytes / dt_single / GiB) if dt_single else None}
+               "single_pass_value": (args.e2e_steps * job_unc_bytes / dt_single / GiB) if dt_single else None,
+               "link": link}
         del h_src, h_dst
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:200]}
@@ -561,6 +593,8 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline and args.op != "hash":
+        os.sched_setaffinity(0, full_affinity)     # the CPU arm gets every core of the host again
+        threads = host_threads()
         try:
             cpu_baseline = cpu_baseline_leg(args, wl, orc, op, n, threads)
         except Exception as ex:  # noqa: BLE001 -- never lose the GPU line because the CPU leg failed
@@ -569,10 +603,11 @@ def main():
     line = {
         "metric": f"{args.codec}_{args.op}_uncompressed_GiB_per_s", "value": value, "unit": "GiB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": f"synthetic batch: {wl['label']}, tiled",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": f"synthetic batch: {wl['label']}, tiled",
         "config": {"workload": f"{args.codec} block {args.op}, {args.block_kib} KiB blocks x {n} batch per GPU" + (" (BASELINE.json configs[1])" if (args.codec, args.op, args.block_kib, n) == ("lz4", "decompress", 64, 65536) else ""),
                    "distinct_blocks": wl["distinct"], "uncompressed_bytes_per_gpu": unc_bytes, "compressed_bytes_per_gpu": comp_bytes,
-                   "ratio": (comp_bytes / unc_bytes) if comp_bytes else None, "parallelism": f"independent blocks, batch per GPU x{world}, no collective",
+                   "ratio": (comp_bytes / unc_bytes) if comp_bytes else None,
+                   "parallelism": (f"independent blocks, batch per GPU x{world}, no collective" if args.scaling == "weak" else f"one batch of {args.blocks} blocks split contiguously over {world} GPUs, no collective"),
                    "l2": "inputs+outputs (>= 4 GiB per step) far exceed the 126 MB L2; no flush needed",
                    "input_streams": "reference algorithm (oracle port of Lz4RawCompressor etc.), prepared untimed"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "single_block": single, "extras": extras, "gpu_launches": int(launches), "clocks": clocks,

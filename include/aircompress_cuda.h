@@ -73,6 +73,11 @@ void     acc_host_free(void *p);
 int32_t  acc_last_error(acc_ctx *ctx, int64_t *offset);  /* status word + offset of the last failed single-block call */
 const char *acc_code_name(int32_t code);
 const char *acc_reason_text(int32_t reason);     /* the reference's exception message for that reason */
+int32_t  acc_device_numa_node(int32_t device);   /* NUMA node of the GPU's PCIe root (sysfs), -1 when unknown */
+int32_t  acc_bind_host_thread(int32_t device);   /* pins the CALLING THREAD to that node's CPUs (call before allocating / pinning the
+                                                    buffers of host-pointer batches: pages are placed by first touch); returns the
+                                                    node, or -1 and changes nothing.  One host thread + one context per device is the
+                                                    multi-GPU model */
 int32_t  acc_sm_count(acc_ctx *ctx);
 int64_t  acc_kernel_launches(acc_ctx *ctx);      /* kernels launched through this ctx so far (bench.py gpu_launches) */
 
