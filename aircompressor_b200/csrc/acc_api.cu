@@ -252,6 +252,9 @@ static bool grow(void **p, int64_t *cap, int64_t need, bool host)
     if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
     cudaError_t e = host ? cudaMallocHost(p, (size_t) ncap) : cudaMalloc(p, (size_t) ncap);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    // device staging starts defined: whole output windows are copied back to the caller (bytes behind the produced length
+    // are unspecified by contract, but they should never be another allocation's leftovers)
+    if (!host) cudaMemset(*p, 0, (size_t) ncap);
     *cap = ncap;
     return true;
 }

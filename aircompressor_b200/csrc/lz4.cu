@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
                 unsigned hits = __ballot_sync(kFull, hit);
                 const int first_hit = hits ? __ffs(hits) - 1 : 31;
                 if (live && lane <= first_hit) table[slot] = (TableT) p;
+                __syncwarp();                                            // the next step's lookups see these inserts
                 if (hits == 0) {
                     pos += 32;
                     continue;

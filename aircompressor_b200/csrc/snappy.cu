@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
                 unsigned hits = __ballot_sync(kFull, hit);
                 const int first_hit = hits ? __ffs(hits) - 1 : 31;
                 if (live && p < 0xffff && lane <= first_hit) table[slot] = (uint16_t) p;
+                __syncwarp();                                            // the next step's lookups see these inserts
                 if (hits == 0) { pos += 32; continue; }
                 const int first = __ffs(hits) - 1;
                 const int64_t mpos = pos + first;

@@ -707,11 +707,17 @@ __global__ void __launch_bounds__(kThreads) zstd_compress_kernel(AccBatch b, uin
                         uint16_t *sb = sbits + (int64_t) k * kMaxSeq;
                         int state = sm.v[V_MODE_OF + k] == 1 ? 0 : fse_begin(nx, dnb, dfs, last_code);
                         sb[nseq - 1] = 0;
+                        // the state is the only loop-carried value: the code of the next step and its two table entries are
+                        // loaded one step ahead, so a step waits for ONE dependent shared-memory load (next_state)
+                        int code = nseq >= 2 ? code_at(nseq - 2) : 0;
+                        int d_nb = dnb[code], d_fs = dfs[code];
                         for (int i = nseq - 2; i >= 0; i--) {
-                            const int code = code_at(i);
-                            const int nb = (int) ((uint32_t) (state + dnb[code]) >> 16);
+                            const int code2 = i > 0 ? code_at(i - 1) : code;
+                            const int d_nb2 = dnb[code2], d_fs2 = dfs[code2];
+                            const int nb = (int) ((uint32_t) (state + d_nb) >> 16);
                             sb[i] = (uint16_t) ((state & ((1 << nb) - 1)) | (nb << 12));
-                            state = nx[(state >> nb) + dfs[code]];
+                            state = nx[(state >> nb) + d_fs];
+                            d_nb = d_nb2; d_fs = d_fs2;
                         }
                         sm.v[V_FINAL_OF + k] = state;
                     }

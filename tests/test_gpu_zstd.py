@@ -108,11 +108,15 @@ def test_decode_error_parity_on_corrupt_frames(engine, oracle, refnative, sample
         else:
             n_bad += 1
             assert status[i] != 0 and (status[i] & 0xFF) == ((-r) & 0xFF), (i, hex(status[i]), hex(-r))
-            n_reason_diff += int(status[i] != -r)
+            if status[i] == -r:
+                assert out_len[i] == off, (i, hex(status[i]), out_len[i], off)     # same reason -> same error offset
+            else:
+                n_reason_diff += 1
         assert (dst[do[i] + caps[i]:do[i] + caps[i] + 64] == 0xA5).all()
     assert n_bad > 20
-    # the reason may differ only where the Java interleaves four Huffman streams (the kernel decodes them independently)
-    assert n_reason_diff <= n_bad // 4, (n_reason_diff, n_bad)
+    # The reason may differ only where the Java interleaves four Huffman streams (the kernel decodes them independently):
+    # measured 0 of 601 corrupted frames (tools/_zerr_probe.py, profiles/README.md); one per hundred is the allowance.
+    assert n_reason_diff <= max(1, n_bad // 100), (n_reason_diff, n_bad)
 
 
 def test_java_shaped_zstd_decompressor(oracle):
