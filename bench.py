@@ -472,8 +472,20 @@ def main():
             return src_t.numel() / (best / 1e3) / 1e9, best
         h2d_gbps, h2d_ms = copy_gbps(src_d, h_src)
         d2h_gbps, d2h_ms = copy_gbps(h_dst, dst_d)
+        # both directions at once (what the overlapped path asks of the link): upload on one stream, download on another
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s_up):
+            ev[0].record(); src_d.copy_(h_src, non_blocking=True); ev[1].record()
+        with torch.cuda.stream(s_dn):
+            ev[2].record(); h_dst.copy_(dst_d, non_blocking=True); ev[3].record()
+        torch.cuda.synchronize()
+        dup_up_ms, dup_dn_ms = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
         link = {"h2d_GBps": h2d_gbps, "d2h_GBps": d2h_gbps, "numa_node": numa_node,
-                "overlap_bound_GiBps": unc_bytes / (max(h2d_ms, d2h_ms) / 1e3) / GiB}
+                "overlap_bound_GiBps": unc_bytes / (max(h2d_ms, d2h_ms) / 1e3) / GiB,
+                "duplex_h2d_GBps": h_src.numel() / (dup_up_ms / 1e3) / 1e9, "duplex_d2h_GBps": dst_d.numel() / (dup_dn_ms / 1e3) / 1e9,
+                "duplex_bound_GiBps": unc_bytes / (max(dup_up_ms, dup_dn_ms) / 1e3) / GiB}
 
         def timed_host_calls(pipeline):
             eng.set_tuning(3, pipeline)
