@@ -37,6 +37,7 @@ struct acc_ctx {
     cudaEvent_t ev_order = nullptr;
     int64_t stats[ACC_STATS_WORDS] = {};
     int tuning_ctas_per_sm = 0;
+    int tuning_decoder = 0;   // LZ4 / Snappy decode: 0 = record path (parse + execute kernels), 1 = the step decoder alone
     int tuning_pipeline = 0;  // host-pointer batches: 0 = auto, 1 = never split, k > 1 = split into k chunks
     // copy streams + events of the pipelined host-pointer path (created on first use)
     static constexpr int kMaxChunks = 16;
@@ -185,6 +186,7 @@ int32_t acc_set_tuning(acc_ctx *c, int32_t key, int32_t value)
 {
     if (!c) return 0;
     if (key == 0) { int prev = c->tuning_ctas_per_sm; c->tuning_ctas_per_sm = value; return prev; }
+    if (key == 1) { int prev = c->tuning_decoder; c->tuning_decoder = value; return prev; }
     if (key == 3) { int prev = c->tuning_pipeline; c->tuning_pipeline = value; return prev; }
     return 0;
 }
@@ -266,9 +268,21 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
     b.work_counter = next_counter(c, st);
     switch (op) {
         case ACC_OP_LZ4_COMPRESS: acc_launch_lz4_compress(b, c->sm_count, st, next_counter(c, st)); c->launches++; break;
-        case ACC_OP_LZ4_DECOMPRESS: acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
+        case ACC_OP_LZ4_DECOMPRESS:
+        case ACC_OP_SNAPPY_DECOMPRESS: {
+            void *scratch = nullptr;
+            unsigned int *second = nullptr;
+            if (c->tuning_decoder != 1) {
+                if (!grow(&c->d_scratch, &c->d_scratch_cap, acc_lz_records_scratch_bytes(b.n), false)) return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
+                scratch = c->d_scratch;
+                second = next_counter(c, st);
+                c->launches++;
+            }
+            if (op == ACC_OP_LZ4_DECOMPRESS) acc_launch_lz4_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st, scratch, second);
+            else acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st, scratch, second);
+            break;
+        }
         case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
-        case ACC_OP_SNAPPY_DECOMPRESS: acc_launch_snappy_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st); break;
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
         case ACC_OP_ZSTD_COMPRESS:
         case ACC_OP_ZSTD_DECOMPRESS: {

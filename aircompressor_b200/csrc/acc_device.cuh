@@ -6,7 +6,11 @@
 // of work is one Compressor/Decompressor call (Compressor.java:18-36, Decompressor.java:18-31).
 #pragma once
 #include <cstdint>
+#ifdef LZS_EMU
+#include "cuda_emu.h"   // host emulation of the record path (tests/host)
+#else
 #include <cuda_runtime.h>
+#endif
 #include "../../include/aircompress_cuda.h"
 
 struct AccBatch {
@@ -27,7 +31,11 @@ struct AccBatch {
 static constexpr int kWarp = 32;
 static constexpr unsigned kFull = 0xffffffffu;
 
+#ifdef LZS_EMU
+__device__ __forceinline__ int lane_id() { return lane_id_emu(); }
+#else
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
 
 __device__ __forceinline__ uint32_t ld_u16le(const uint8_t *p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8); }
 
@@ -130,9 +138,10 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *dst, int64_t offset, in
 }
 
 // kernel launchers implemented in the per-codec translation units
-void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st);
+void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, unsigned int *second_counter);
+int64_t acc_lz_records_scratch_bytes(int64_t n);   // record path of the LZ4 / Snappy decoders (lz_records.cuh); scratch == nullptr: step decoder alone
 void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, unsigned int *second_counter);
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st);
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, unsigned int *second_counter);
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st);
 void acc_launch_xxh64(const AccBatch &b, uint64_t seed, int sm_count, cudaStream_t st);
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes);

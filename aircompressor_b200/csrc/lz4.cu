@@ -7,6 +7,7 @@
 // AbstractTestCompression.java:362-393).
 #include "acc_device.cuh"
 #include "lz4_decode_v1.cuh"
+#include "lz4_records.cuh"
 
 namespace {
 
@@ -193,12 +194,64 @@ __global__ void __launch_bounds__(kLz4WarpsPerCta * 32) lz4_compress_kernel(AccB
     }
 }
 
+
+// ---- record path (lz_records.cuh): parse kernel (one lane per block) + execute kernel (one warp per block) ----
+constexpr int kParseThreads = 256;
+
+__global__ void __launch_bounds__(kParseThreads) lz4_parse_kernel(AccBatch b, uint2 *recs, lzs::RecHeader *hdrs, int row)
+{
+    __shared__ __align__(16) uint8_t win[kParseThreads * lzs::kWinStride];
+    lzs::parse_lane<Lz4Records>(b, win + threadIdx.x * lzs::kWinStride, recs, hdrs, row);
+}
+
+__global__ void __launch_bounds__(256, 6) lz4_execute_kernel(AccBatch b, const uint2 *recs, const lzs::RecHeader *hdrs, int row)
+{
+    lzs::execute_warp<Lz4Records>(b, recs, hdrs, row, lane_id());
+}
+
 }  // namespace
 
-void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
+// scratch of the record path for a batch of n blocks: one header + one row of records per block.  Rows hold up to 32,768
+// records and share about 4 GiB (a 64 KiB Silesia block has ~4,000 sequences; a block with more than its row holds
+// resumes the step decoder there)
+int64_t acc_lz_records_row(int64_t n)
 {
-    // warp-per-block step decoder: multi-sequence + medium steps, registers bounded for 8 resident CTAs (32 registers,
-    // 64 warps per SM)
+    int64_t row = (4LL << 30) / 8 / (n > 0 ? n : 1);
+    if (row > 32768) row = 32768;
+    if (row < 256) row = 256;
+    return row;
+}
+int64_t acc_lz_records_scratch_bytes(int64_t n) { return n * ((int64_t) sizeof(lzs::RecHeader) + acc_lz_records_row(n) * 8) + 256; }
+
+namespace {
+template <class ParseK, class ExecK>
+void launch_record_path(ParseK parse_k, ExecK exec_k, const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, unsigned int *second_counter)
+{
+    const int row = (int) acc_lz_records_row(b.n);
+    lzs::RecHeader *hdrs = reinterpret_cast<lzs::RecHeader *>(scratch);
+    uint2 *recs = reinterpret_cast<uint2 *>(hdrs + b.n);
+    // parse: one thread per block, all blocks at once when they fit the machine (2048 threads per SM)
+    int64_t pctas = (b.n + kParseThreads - 1) / kParseThreads;
+    const int64_t pmax = (int64_t) sm_count * (2048 / kParseThreads);
+    if (pctas > pmax) pctas = pmax;
+    if (pctas < 1) pctas = 1;
+    parse_k<<<(unsigned) pctas, kParseThreads, 0, st>>>(b, recs, hdrs, row);
+    // execute: one warp per block, persistent
+    AccBatch b2 = b;
+    b2.work_counter = second_counter;
+    int64_t ectas = (b.n + 7) / 8;
+    const int64_t emax = (int64_t) sm_count * 6;
+    if (ectas > emax) ectas = emax;
+    if (ectas < 1) ectas = 1;
+    exec_k<<<(unsigned) ectas, 256, 0, st>>>(b2, recs, hdrs, row);
+}
+}  // namespace
+
+void acc_launch_lz4_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, unsigned int *second_counter)
+{
+    if (scratch) { launch_record_path(lz4_parse_kernel, lz4_execute_kernel, b, sm_count, st, scratch, second_counter); return; }
+    // the step decoder alone (acc_set_tuning key 1): multi-sequence + medium steps, registers bounded for 8 resident CTAs
+    // (32 registers, 64 warps per SM)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;

@@ -177,10 +177,46 @@ __global__ void __launch_bounds__(kSnWarpsPerCta * 32) snappy_compress_kernel(Ac
     }
 }
 
+
+// ---- record path (lz_records.cuh) ----
+constexpr int kParseThreads = 256;
+
+__global__ void __launch_bounds__(kParseThreads) snappy_parse_kernel(AccBatch b, uint2 *recs, lzs::RecHeader *hdrs, int row)
+{
+    __shared__ __align__(16) uint8_t win[kParseThreads * lzs::kWinStride];
+    lzs::parse_lane<SnappyRecords>(b, win + threadIdx.x * lzs::kWinStride, recs, hdrs, row);
+}
+
+__global__ void __launch_bounds__(256, 5) snappy_execute_kernel(AccBatch b, const uint2 *recs, const lzs::RecHeader *hdrs, int row)
+{
+    lzs::execute_warp<SnappyRecords>(b, recs, hdrs, row, lane_id());
+}
+
 }  // namespace
 
-void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st)
+int64_t acc_lz_records_row(int64_t n);   // lz4.cu
+
+void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, unsigned int *second_counter)
 {
+    if (scratch) {
+        const int row = (int) acc_lz_records_row(b.n);
+        lzs::RecHeader *hdrs = reinterpret_cast<lzs::RecHeader *>(scratch);
+        uint2 *recs = reinterpret_cast<uint2 *>(hdrs + b.n);
+        int64_t pctas = (b.n + kParseThreads - 1) / kParseThreads;
+        const int64_t pmax = (int64_t) sm_count * (2048 / kParseThreads);
+        if (pctas > pmax) pctas = pmax;
+        if (pctas < 1) pctas = 1;
+        snappy_parse_kernel<<<(unsigned) pctas, kParseThreads, 0, st>>>(b, recs, hdrs, row);
+        AccBatch b2 = b;
+        b2.work_counter = second_counter;
+        int64_t ectas = (b.n + 7) / 8;
+        const int64_t emax = (int64_t) sm_count * 5;
+        if (ectas > emax) ectas = emax;
+        if (ectas < 1) ectas = 1;
+        snappy_execute_kernel<<<(unsigned) ectas, 256, 0, st>>>(b2, recs, hdrs, row);
+        return;
+    }
+    // the step decoder alone (acc_set_tuning key 1)
     if (ctas_per_sm <= 0) ctas_per_sm = 8;
     int64_t ctas = (b.n + 7) / 8;
     int64_t max_ctas = (int64_t) sm_count * ctas_per_sm;

@@ -41,10 +41,13 @@ def _gpu_decompress(engine, codec, streams, caps, guard=0):
     return dst, do, out_len, status
 
 
-@pytest.fixture
-def decoder(engine):
-    """one LZ4 / Snappy decode kernel ships (the warp-per-block step decoder); the fixture is kept so the tests read the same"""
-    return 0
+@pytest.fixture(params=[0, 1], ids=["record-path", "step-decoder"])
+def decoder(request, engine):
+    """the decode tests run against the record path (parse + execute kernels, lz_records.cuh: the default) and against the step
+    decoder alone (acc_set_tuning key 1), which is also what every block's tail resumes in"""
+    engine.set_tuning(1, request.param)
+    yield request.param
+    engine.set_tuning(1, 0)
 
 
 @pytest.mark.parametrize("codec", ["lz4", "snappy"])
