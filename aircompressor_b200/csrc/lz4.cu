@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kParseThreads) lz4_parse_kernel(AccBatch b, ui
 
 __global__ void __launch_bounds__(256, 6) lz4_execute_kernel(AccBatch b, const uint2 *recs, const lzs::RecHeader *hdrs, int row)
 {
-    lzs::execute_warp<Lz4Records>(b, recs, hdrs, row, lane_id());
+    __shared__ __align__(16) uint8_t rings[8 * lzs::kOutRing];
+    lzs::execute_warp<Lz4Records>(b, recs, hdrs, row, rings + (threadIdx.x >> 5) * lzs::kOutRing, lane_id());
 }
 
 }  // namespace

@@ -35,6 +35,7 @@ struct Lz4Records {
                 const int32_t ip = P.ip;
                 P.tok_ip = ip; P.tok_op = P.op;
                 if (ip >= safe_end) return lzs::kFallback;
+                C.ensure(ip);                                // token, a short literal run's offset and one extension byte lie within 32 bytes
                 const uint32_t tok = C.byte(ip);
                 uint32_t ll = tok >> 4;
                 int32_t p = ip + 1;
@@ -43,6 +44,7 @@ struct Lz4Records {
                     int cnt = 0;
                     do {
                         if (p >= safe_end || ++cnt > 64) return lzs::kFallback;
+                        C.ensure(p);
                         v = C.byte(p++);
                         ll += v;
                     }
@@ -64,6 +66,7 @@ struct Lz4Records {
             // mode 2: offset, match length
             const int32_t mpos = P.mpos;
             if (mpos + 2 > safe_end) return lzs::kFallback;
+            if (P.pll == 0) C.ensure(mpos);                  // behind a long literal run; otherwise still inside the token's 32 bytes
             const uint32_t off = C.byte(mpos) | (C.byte(mpos + 1) << 8);
             uint32_t ml = P.tok_ml;
             int32_t p2 = mpos + 2;
@@ -71,6 +74,7 @@ struct Lz4Records {
                 uint32_t v;
                 do {
                     if (p2 >= safe_end || ml > (1u << 19)) return lzs::kFallback;
+                    C.ensure(p2);
                     v = C.byte(p2++);
                     ml += v;
                 }

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(kParseThreads) snappy_parse_kernel(AccBatch b,
 
 __global__ void __launch_bounds__(256, 5) snappy_execute_kernel(AccBatch b, const uint2 *recs, const lzs::RecHeader *hdrs, int row)
 {
-    lzs::execute_warp<SnappyRecords>(b, recs, hdrs, row, lane_id());
+    __shared__ __align__(16) uint8_t rings[8 * lzs::kOutRing];
+    lzs::execute_warp<SnappyRecords>(b, recs, hdrs, row, rings + (threadIdx.x >> 5) * lzs::kOutRing, lane_id());
 }
 
 }  // namespace

@@ -248,6 +248,7 @@ struct SnappyRecords {
             // varint preamble: in_len >= 32 here, so its <= 5 bytes exist
             uint32_t result = 0;
             int n = 0;
+            C.ensure(0);
             for (int shift = 0;; shift += 7) {
                 const uint32_t v = C.byte(n++);
                 result |= (v & 0x7f) << shift;
@@ -258,6 +259,7 @@ struct SnappyRecords {
             C.in += n;                 // positions from here on are relative to the first element
             C.in_len -= n;
             C.head = (uint32_t) ((uintptr_t) C.in & 31);
+            C.win_chunks = (C.head + (uint32_t) C.in_len + 31) >> 5;
             C.win_tag = ~0u;
             P.mode = 1;
         }
@@ -273,6 +275,7 @@ struct SnappyRecords {
             const int32_t ip = P.ip;
             P.el_ip = ip; P.el_op = P.op;
             if (ip >= safe_end) return lzs::kFallback;
+            C.ensure(ip);                                    // the tag and its <= 4 trailer bytes
             const uint32_t tag = C.byte(ip);
             if ((tag & 3) == 0) {
                 const uint32_t hi = tag >> 2;
@@ -294,6 +297,7 @@ struct SnappyRecords {
                 // short literal: take the copy behind it into the same record when there is one
                 const int32_t q = p + (int32_t) ll;
                 if (q < safe_end) {
+                    C.ensure(q);                             // the literal's bytes are skipped, not read: the window moves on
                     const uint32_t t2 = C.byte(q);
                     const uint32_t k2 = t2 & 3;
                     if (k2 == 1 || k2 == 2) {

@@ -61,6 +61,16 @@ static inline unsigned __ballot_sync(unsigned, bool p)
     __syncwarp();
     return m;
 }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    t_warp->xchg[t_lane] = v;
+    __syncwarp();
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned) t_warp->xchg[i];
+    __syncwarp();
+    return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 [[noreturn]] static inline void emu_unsupported(const char *what) { fprintf(stderr, "cuda_emu: %s reached\n", what); abort(); }

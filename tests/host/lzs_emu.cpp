@@ -39,11 +39,12 @@ static void run(AccBatch b, int row, long *n_records)
     {   // stage 2: execute
         b.work_counter = &c2;
         EmuWarp warps[kWarps];
+        static uint8_t rings[kWarps][lzs::kOutRing] __attribute__((aligned(16)));
         for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
         std::vector<std::thread> th;
         for (int w = 0; w < kWarps; w++)
             for (int l = 0; l < 32; l++)
-                th.emplace_back([&, w, l] { t_warp = &warps[w]; t_lane = l; lzs::execute_warp<Codec>(b, recs.data(), hdrs.data(), row, l); });
+                th.emplace_back([&, w, l] { t_warp = &warps[w]; t_lane = l; lzs::execute_warp<Codec>(b, recs.data(), hdrs.data(), row, rings[w], l); });
         for (auto &t : th) t.join();
     }
 }
