@@ -233,18 +233,18 @@ __device__ __forceinline__ void snappy_decode_block(const uint8_t *__restrict__ 
 struct SnappyRecords {
     struct Parse {
         int32_t ip, op;            // next element, next output byte (positions behind the preamble)
-        int32_t el_ip, el_op;      // restart point of a fallback (el_ip == -1: the whole block)
-        int32_t lit_pos, lit_rem;  // mode 2: rest of a long literal, handed over in pieces
-        uint32_t mode;             // 0 preamble, 1 element, 2 long literal
+        int32_t el_ip, el_op;      // where the step decoder takes over: the element that was not recorded (el_ip == -1: the whole block)
+        bool started;              // the preamble has been read
     };
-    static __device__ __forceinline__ void begin(Parse &P) { P.ip = 0; P.op = 0; P.el_ip = -1; P.el_op = 0; P.lit_pos = 0; P.lit_rem = 0; P.mode = 0; }
-    // where the step decoder takes over: the element that was not (completely) recorded; -1 = the whole block
+    static __device__ __forceinline__ void begin(Parse &P) { P.ip = 0; P.op = 0; P.el_ip = -1; P.el_op = 0; P.started = false; }
     static __device__ __forceinline__ uint32_t resume_ip(const Parse &P) { return (uint32_t) P.el_ip; }
     static __device__ __forceinline__ uint32_t resume_op(const Parse &P) { return (uint32_t) P.el_op; }
 
-    static __device__ __forceinline__ int parse_run(Parse &P, lzs::ParseCtx &C, const int budget)
+    // One element (or a literal of <= 60 bytes with the 1- / 2-byte-offset copy behind it): all checks, then its record(s).
+    // Nothing is recorded before the element is known to be valid, so a hand-over always happens at an element.
+    static __device__ __forceinline__ int parse_one(Parse &P, lzs::ParseCtx &C, const int row)
     {
-        if (P.mode == 0) {
+        if (!P.started) {
             // varint preamble: in_len >= 32 here, so its <= 5 bytes exist
             uint32_t result = 0;
             int n = 0;
@@ -261,83 +261,83 @@ struct SnappyRecords {
             C.head = (uint32_t) ((uintptr_t) C.in & 31);
             C.win_chunks = (C.head + (uint32_t) C.in_len + 31) >> 5;
             C.win_tag = ~0u;
-            P.mode = 1;
+            P.started = true;
         }
         const int32_t safe_end = C.in_len - 16;
-        while (C.n_rec < budget) {
-            if (P.mode == 2) {
-                const int32_t n = P.lit_rem < lzs::kMaxLitPiece ? P.lit_rem : lzs::kMaxLitPiece;
-                if (!C.emit(P.lit_pos, (uint32_t) n, 0, lzs::kNoOffset)) return lzs::kFallback;
-                P.lit_pos += n; P.lit_rem -= n; P.op += n;
-                if (P.lit_rem == 0) { P.ip = P.lit_pos; P.mode = 1; }
-                continue;
+        const int32_t ip = P.ip;
+        P.el_ip = ip; P.el_op = P.op;
+        if (C.n_rec + 2 > row) return lzs::kRowFull;
+        if (ip >= safe_end) return lzs::kFallback;
+        C.ensure(ip);                                    // the tag and its <= 4 trailer bytes
+        const uint32_t tag = C.byte(ip);
+        if ((tag & 3) == 0) {
+            const uint32_t hi = tag >> 2;
+            int32_t p = ip + 1;
+            uint32_t ll = hi + 1;
+            if (hi >= 60) {
+                const int nb = (int) hi - 59;
+                uint32_t v = 0;
+                for (int i = 0; i < nb; i++) v |= C.byte(p + i) << (8 * i);
+                p += nb;
+                if (v >= (1u << 24)) return lzs::kFallback;
+                ll = v + 1;
             }
-            const int32_t ip = P.ip;
-            P.el_ip = ip; P.el_op = P.op;
-            if (ip >= safe_end) return lzs::kFallback;
-            C.ensure(ip);                                    // the tag and its <= 4 trailer bytes
-            const uint32_t tag = C.byte(ip);
-            if ((tag & 3) == 0) {
-                const uint32_t hi = tag >> 2;
-                int32_t p = ip + 1;
-                uint32_t ll = hi + 1;
-                if (hi >= 60) {
-                    const int nb = (int) hi - 59;
-                    uint32_t v = 0;
-                    for (int i = 0; i < nb; i++) v |= C.byte(p + i) << (8 * i);
-                    p += nb;
-                    if (v >= (1u << 24)) return lzs::kFallback;
-                    ll = v + 1;
+            if (p + (int32_t) ll + 8 > C.in_len || P.op + (int32_t) ll + 8 > C.out_cap) return lzs::kFallback;
+            if (hi >= 60) {
+                // a long literal travels as literal-only records (12-bit length field)
+                int32_t lp = p, rem = (int32_t) ll;
+                while (rem > 0) {
+                    if (C.n_rec + 2 > row) return lzs::kRowFull;       // the pieces already recorded are written again by the step decoder: same bytes
+                    const int32_t n = rem < lzs::kMaxLitPiece ? rem : lzs::kMaxLitPiece;
+                    if (!C.emit(lp, (uint32_t) n, 0, lzs::kNoOffset)) return lzs::kFallback;
+                    lp += n; rem -= n;
                 }
-                if (p + (int32_t) ll + 8 > C.in_len || P.op + (int32_t) ll + 8 > C.out_cap) return lzs::kFallback;
-                if (hi >= 60) {
-                    P.lit_pos = p; P.lit_rem = (int32_t) ll; P.mode = 2;
-                    continue;
-                }
-                // short literal: take the copy behind it into the same record when there is one
-                const int32_t q = p + (int32_t) ll;
-                if (q < safe_end) {
-                    C.ensure(q);                             // the literal's bytes are skipped, not read: the window moves on
-                    const uint32_t t2 = C.byte(q);
-                    const uint32_t k2 = t2 & 3;
-                    if (k2 == 1 || k2 == 2) {
-                        const uint32_t b1 = C.byte(q + 1);
-                        uint32_t ml, off;
-                        int32_t adv;
-                        if (k2 == 1) { ml = 4 + ((t2 >> 2) & 7); off = ((t2 >> 5) << 8) | b1; adv = 2; }
-                        else { ml = (t2 >> 2) + 1; off = b1 | (C.byte(q + 2) << 8); adv = 3; }
-                        const int32_t mop = P.op + (int32_t) ll;
-                        if (off != 0 && (int32_t) off <= mop && mop + (int32_t) ml + 8 <= C.out_cap) {
-                            if (!C.emit(p, ll, ml, off)) return lzs::kFallback;
-                            P.ip = q + adv;
-                            P.op = mop + (int32_t) ml;
-                            continue;
-                        }
+                P.ip = p + (int32_t) ll;
+                P.op += (int32_t) ll;
+                return lzs::kMore;
+            }
+            // short literal: take the copy behind it into the same record when there is one
+            const int32_t q = p + (int32_t) ll;
+            if (q < safe_end) {
+                C.ensure(q);                             // the literal's bytes are skipped, not read: the window moves on
+                const uint32_t t2 = C.byte(q);
+                const uint32_t k2 = t2 & 3;
+                if (k2 == 1 || k2 == 2) {
+                    const uint32_t b1 = C.byte(q + 1);
+                    uint32_t ml, off;
+                    int32_t adv;
+                    if (k2 == 1) { ml = 4 + ((t2 >> 2) & 7); off = ((t2 >> 5) << 8) | b1; adv = 2; }
+                    else { ml = (t2 >> 2) + 1; off = b1 | (C.byte(q + 2) << 8); adv = 3; }
+                    const int32_t mop = P.op + (int32_t) ll;
+                    if (off != 0 && (int32_t) off <= mop && mop + (int32_t) ml + 8 <= C.out_cap) {
+                        if (!C.emit(p, ll, ml, off)) return lzs::kFallback;
+                        P.ip = q + adv;
+                        P.op = mop + (int32_t) ml;
+                        return lzs::kMore;
                     }
                 }
-                if (!C.emit(p, ll, 0, lzs::kNoOffset)) return lzs::kFallback;
-                P.ip = q;
-                P.op += (int32_t) ll;
-                continue;
             }
-            const uint32_t kind = tag & 3;
-            const uint32_t b1 = C.byte(ip + 1);
-            uint32_t ml, off;
-            int32_t adv;
-            if (kind == 1) { ml = 4 + ((tag >> 2) & 7); off = ((tag >> 5) << 8) | b1; adv = 2; }
-            else if (kind == 2) { ml = (tag >> 2) + 1; off = b1 | (C.byte(ip + 2) << 8); adv = 3; }
-            else {
-                ml = (tag >> 2) + 1;
-                off = b1 | (C.byte(ip + 2) << 8) | (C.byte(ip + 3) << 16) | (C.byte(ip + 4) << 24);
-                adv = 5;
-            }
-            if (off == 0 || off > (uint32_t) P.op || P.op + (int32_t) ml + 8 > C.out_cap) return lzs::kFallback;
-            if (!C.emit(ip, 0, ml, off)) return lzs::kFallback;
-            P.ip = ip + adv;
-            P.op += (int32_t) ml;
+            if (!C.emit(p, ll, 0, lzs::kNoOffset)) return lzs::kFallback;
+            P.ip = q;
+            P.op += (int32_t) ll;
+            return lzs::kMore;
         }
-        if (P.mode == 1) { P.el_ip = P.ip; P.el_op = P.op; }      // row full between two elements: the next element is the resume point
-        return lzs::kRowFull;
+        const uint32_t kind = tag & 3;
+        const uint32_t b1 = C.byte(ip + 1);
+        uint32_t ml, off;
+        int32_t adv;
+        if (kind == 1) { ml = 4 + ((tag >> 2) & 7); off = ((tag >> 5) << 8) | b1; adv = 2; }
+        else if (kind == 2) { ml = (tag >> 2) + 1; off = b1 | (C.byte(ip + 2) << 8); adv = 3; }
+        else {
+            ml = (tag >> 2) + 1;
+            off = b1 | (C.byte(ip + 2) << 8) | (C.byte(ip + 3) << 16) | (C.byte(ip + 4) << 24);
+            adv = 5;
+        }
+        if (off == 0 || off > (uint32_t) P.op || P.op + (int32_t) ml + 8 > C.out_cap) return lzs::kFallback;
+        if (!C.emit(ip, 0, ml, off)) return lzs::kFallback;
+        P.ip = ip + adv;
+        P.op += (int32_t) ml;
+        return lzs::kMore;
     }
 
     // the step decoder resumes at the element at (ip, op); writes out_len / status

@@ -29,6 +29,7 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y =
 
 struct EmuWarp {
     pthread_barrier_t bar;
+    int nlanes = 32;            // threads that play this warp (the barrier's count)
     volatile unsigned long long xchg[32];
 };
 extern thread_local EmuWarp *t_warp;
@@ -57,7 +58,7 @@ static inline unsigned __ballot_sync(unsigned, bool p)
     t_warp->xchg[t_lane] = p ? 1 : 0;
     __syncwarp();
     unsigned m = 0;
-    for (int i = 0; i < 32; i++) m |= (unsigned) (t_warp->xchg[i] & 1) << i;
+    for (int i = 0; i < t_warp->nlanes; i++) m |= (unsigned) (t_warp->xchg[i] & 1) << i;
     __syncwarp();
     return m;
 }
@@ -72,6 +73,7 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v)
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
+static inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, !p) == 0; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 [[noreturn]] static inline void emu_unsupported(const char *what) { fprintf(stderr, "cuda_emu: %s reached\n", what); abort(); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

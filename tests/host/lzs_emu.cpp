@@ -31,8 +31,11 @@ static void run(AccBatch b, int row, long *n_records)
     {   // stage 1: parse
         b.work_counter = &c1;
         static uint8_t win[kParseLanes][lzs::kWinStride] __attribute__((aligned(16)));
+        EmuWarp pw;                                       // the parse lanes run their rounds in lockstep like the lanes of a warp
+        pw.nlanes = kParseLanes;
+        pthread_barrier_init(&pw.bar, nullptr, kParseLanes);
         std::vector<std::thread> th;
-        for (int l = 0; l < kParseLanes; l++) th.emplace_back([&, l] { lzs::parse_lane<Codec>(b, win[l], recs.data(), hdrs.data(), row); });
+        for (int l = 0; l < kParseLanes; l++) th.emplace_back([&, l] { t_warp = &pw; t_lane = l; lzs::parse_lane<Codec>(b, win[l], recs.data(), hdrs.data(), row); });
         for (auto &t : th) t.join();
     }
     for (auto &h : hdrs) *n_records += h.n_rec;
