@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short per-codec side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--decode-path", type=int, default=0, help="LZ4 / Snappy decode: 0 library default, 1 step decoder, 2 record path")
     ap.add_argument("--pipeline", type=int, default=0, help="host-pointer path: 0 auto, 1 single pass, k>1 overlapped runs")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: ONE batch of --blocks blocks is split over the ranks (contiguous, byte-balanced: BASELINE.md s3 config 3 wording)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
@@ -403,6 +404,8 @@ def main():
     eng = acb.BatchEngine(local_rank)
     if args.ctas_per_sm:
         eng.set_tuning(0, args.ctas_per_sm)
+    if args.decode_path:
+        eng.set_tuning(1, args.decode_path)
     op = CODEC_OPS[(args.codec, args.op)]
     n = args.blocks
     if args.scaling == "strong" and world > 1:

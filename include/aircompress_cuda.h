@@ -171,6 +171,8 @@ int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t 
 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
  * key 0: resident CTAs per SM for the warp-per-block decode kernels;
+ * key 1: LZ4 / Snappy decode path: 1 = the step decoder (one warp walks and copies a block), 2 = the record path (parse kernel +
+ *        execute kernel, csrc/lz_records.cuh), 0 = the faster of the two per codec (measured: LZ4 -> 1, Snappy -> 2);
  * key 3: host-pointer batches, 1 = never split, k > 1 = split into k overlapped upload/kernel/download runs
  * (default: automatic, up to 16 runs of >= 4096 blocks and >= 32 MiB each); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);

@@ -41,9 +41,13 @@ def test_every_block_of_the_corpus(engine, oracle, corpus_files, codec, block_ki
     fails, rlen = oracle.batch(orc_c, src, so, sl, ref, do, caps, threads=threads)
     assert fails == 0
     back = np.full(len(src) + 64, 0x3C, dtype=np.uint8)
-    dlen, st = engine.run_host(gpu_d, ref, do, rlen, back, so, sl)
-    assert (st == 0).all() and (dlen == sl).all()
-    assert np.array_equal(back[:len(src)], src) and (back[len(src):] == 0x3C).all()
+    for path in ((1, 2) if codec != "zstd" else (0,)):          # LZ4 / Snappy: the step decoder and the record path (acc_set_tuning key 1)
+        engine.set_tuning(1, path)
+        back[:] = 0x3C
+        dlen, st = engine.run_host(gpu_d, ref, do, rlen, back, so, sl)
+        engine.set_tuning(1, 0)
+        assert (st == 0).all() and (dlen == sl).all(), path
+        assert np.array_equal(back[:len(src)], src) and (back[len(src):] == 0x3C).all(), path
 
     # ---- encode: GPU streams -> oracle decoder (Java decoder rules, exact-size outputs) ----
     comp = np.zeros(int(bound * n), dtype=np.uint8)

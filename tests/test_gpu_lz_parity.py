@@ -41,10 +41,10 @@ def _gpu_decompress(engine, codec, streams, caps, guard=0):
     return dst, do, out_len, status
 
 
-@pytest.fixture(params=[0, 1], ids=["record-path", "step-decoder"])
+@pytest.fixture(params=[2, 1], ids=["record-path", "step-decoder"])
 def decoder(request, engine):
-    """the decode tests run against the record path (parse + execute kernels, lz_records.cuh: the default) and against the step
-    decoder alone (acc_set_tuning key 1), which is also what every block's tail resumes in"""
+    """the decode tests run against the record path (parse + execute kernels, lz_records.cuh: Snappy's default) and against the
+    step decoder alone (LZ4's default, and what every block's tail resumes in); acc_set_tuning key 1"""
     engine.set_tuning(1, request.param)
     yield request.param
     engine.set_tuning(1, 0)
