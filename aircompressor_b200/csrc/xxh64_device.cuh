@@ -41,7 +41,19 @@ __device__ __forceinline__ uint64_t xxh64_group4(const uint8_t *in, int64_t len,
             for (; s < stripes; s++) v = mix(v, q[s * 4]);
         }
         else {
-            for (int64_t s = 0; s < stripes; s++) v = mix(v, ld_u64_unaligned(p + s * 32));
+            // any other alignment (blocks packed behind a ragged one): aligned 8-byte words, each value assembled from two of
+            // them -- the same number of independent loads in flight as the aligned loop instead of a chain of 4-byte loads
+            const uintptr_t a = (uintptr_t) p;
+            const uint32_t sh = (uint32_t) (a & 7) * 8;                 // != 0 here
+            const uint64_t *q = (const uint64_t *) (a & ~(uintptr_t) 7);
+            int64_t s = 0;
+            for (; s + 4 <= stripes; s += 4) {
+                const uint64_t l0 = q[(s + 0) * 4], h0 = q[(s + 0) * 4 + 1], l1 = q[(s + 1) * 4], h1 = q[(s + 1) * 4 + 1];
+                const uint64_t l2 = q[(s + 2) * 4], h2 = q[(s + 2) * 4 + 1], l3 = q[(s + 3) * 4], h3 = q[(s + 3) * 4 + 1];
+                v = mix(v, (l0 >> sh) | (h0 << (64 - sh))); v = mix(v, (l1 >> sh) | (h1 << (64 - sh)));
+                v = mix(v, (l2 >> sh) | (h2 << (64 - sh))); v = mix(v, (l3 >> sh) | (h3 << (64 - sh)));
+            }
+            for (; s < stripes; s++) v = mix(v, (q[s * 4] >> sh) | (q[s * 4 + 1] << (64 - sh)));
         }
         // gather the four accumulators of the group
         const int lane = lane_id();

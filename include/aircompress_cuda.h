@@ -144,9 +144,10 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
  * every launch takes one or two of the context's 256 work-stealing counters, which are reused round-robin).
  * Batches of ONE context are ordered: a batch enqueued on a different stream than the previous one first waits for
  * it (the context's scratch and counters are shared), so use one context per concurrent stream of work.
- * Device buffers: kernels read whole aligned 4-byte words, i.e. up to 3 bytes in front of / behind a block's
- * [src_off, src_off + src_len) range -- never beyond the 4-byte-aligned extent of src_base's allocation (cudaMalloc
- * sizes are multiples of 256 bytes), so pad a sub-allocated source buffer to a multiple of 4 bytes.
+ * Device buffers: kernels read whole aligned words (4 bytes; 8 in the XXH64 kernel, 32 in the parse kernel of the record
+ * path), i.e. a few bytes in front of / behind a block's [src_off, src_off + src_len) range -- never beyond the
+ * 32-byte-aligned extent of src_base's allocation (cudaMalloc sizes are multiples of 256 bytes), so pad a sub-allocated
+ * source buffer to a multiple of 32 bytes.
  * Without it the library copies host->device,
  * runs, copies results back and synchronises before returning; large batches are cut into runs of consecutive
  * blocks whose upload, kernel and download overlap (see acc_set_tuning key 3).
@@ -172,7 +173,8 @@ int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
  * key 0: resident CTAs per SM for the warp-per-block decode kernels;
  * key 1: LZ4 / Snappy decode path: 1 = the step decoder (one warp walks and copies a block), 2 = the record path (parse kernel +
- *        execute kernel, csrc/lz_records.cuh), 0 = the faster of the two per codec (measured: LZ4 -> 1, Snappy -> 2);
+ *        execute kernel, csrc/lz_records.cuh), 0 = automatic (the record path for Snappy batches of >= 49,152 blocks, where its
+ *        fixed parse latency is paid back; the step decoder otherwise);
  * key 3: host-pointer batches, 1 = never split, k > 1 = split into k overlapped upload/kernel/download runs
  * (default: automatic, up to 16 runs of >= 4096 blocks and >= 32 MiB each); other keys are ignored. */
 int32_t acc_set_tuning(acc_ctx *ctx, int32_t key, int32_t value);
