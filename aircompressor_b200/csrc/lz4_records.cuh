@@ -30,55 +30,60 @@ struct Lz4Records {
         const int32_t ip = P.ip;
         P.tok_ip = ip; P.tok_op = P.op;
         if (C.n_rec + 2 > row) return lzs::kRowFull;
-        if (ip >= safe_end) return lzs::kFallback;
-        C.ensure(ip);                                // token, a short literal run's offset and the first extension bytes lie within 32 bytes
+        if (ip + 20 > safe_end) return lzs::kFallback;   // token + extension + 14 literals + offset + extension of a short sequence: all readable
+        C.ensure(ip);                                // ... and all within the 32 bytes the window guarantees
         const uint32_t tok = C.byte(ip);
-        uint32_t ll = tok >> 4, ml = tok & 15;
-        int32_t p = ip + 1;
-        if (ll == 15) {
-            if (p >= safe_end) return lzs::kFallback;
-            uint32_t v = C.byte(p++);
-            ll += v;
-            for (int cnt = 0; v == 255; ) {          // rare: further extension bytes
+        // the first extension byte of either length is read whether the token asks for it or not: the common sequence (at most
+        // one extension byte per length) is straight-line code, which is what keeps the 32 lanes of the warp together
+        const bool lx = tok >= 0xF0;
+        const uint32_t e1 = C.byte(ip + 1);
+        uint32_t ll = (tok >> 4) + (lx ? e1 : 0u);
+        int32_t p = ip + 1 + (lx ? 1 : 0);
+        if (lx && e1 == 255) {                       // rare: further extension bytes
+            uint32_t v;
+            int cnt = 0;
+            do {
                 if (p >= safe_end || ++cnt > 64) return lzs::kFallback;
                 C.ensure(p);
                 v = C.byte(p++);
                 ll += v;
             }
+            while (v == 255);
         }
         if (p + (int32_t) ll + 8 > C.in_len || P.op + (int32_t) ll + 12 > C.out_cap) return lzs::kFallback;
         const int32_t mpos = p + (int32_t) ll;
-        if (mpos + 2 > safe_end) return lzs::kFallback;
-        if (tok >= 0xF0) C.ensure(mpos);             // behind a long literal run the window moves on
+        if (mpos + 4 > safe_end) return lzs::kFallback;
+        if (lx) C.ensure(mpos);                      // behind a long literal run the window moves on
         const uint32_t off = C.byte(mpos) | (C.byte(mpos + 1) << 8);
-        int32_t p2 = mpos + 2;
-        if (ml == 15) {
-            if (p2 >= safe_end) return lzs::kFallback;
-            C.ensure(p2);
-            uint32_t v = C.byte(p2++);
-            ml += v;
-            while (v == 255) {                       // rare
+        const bool mx = (tok & 15) == 15;
+        const uint32_t e2 = C.byte(mpos + 2);
+        uint32_t ml = (tok & 15) + (mx ? e2 : 0u);
+        int32_t p2 = mpos + 2 + (mx ? 1 : 0);
+        if (mx && e2 == 255) {                       // rare
+            uint32_t v;
+            do {
                 if (p2 >= safe_end || ml > (1u << 19)) return lzs::kFallback;
                 C.ensure(p2);
                 v = C.byte(p2++);
                 ml += v;
             }
+            while (v == 255);
         }
         ml += kMinMatch;
         const int32_t mop = P.op + (int32_t) ll;     // output position of the match
         if (off == 0 || (int32_t) off > mop || mop + (int32_t) ml + 12 > C.out_cap) return lzs::kFallback;
-        if (tok >= 0xF0) {
-            // a long literal run travels as literal-only records (12-bit length field), the match follows on its own
+        if (lx && ll > (uint32_t) lzs::kMaxLitPiece) {
+            // rare: a literal run beyond the 12-bit length field travels as several literal-only records
             int32_t lp = p, rem = (int32_t) ll;
-            while (rem > 0) {
-                if (C.n_rec + 2 > row) return lzs::kRowFull;           // the pieces already recorded are written again by the step decoder: same bytes
-                const int32_t n = rem < lzs::kMaxLitPiece ? rem : lzs::kMaxLitPiece;
-                if (!C.emit(lp, (uint32_t) n, 0, lzs::kNoOffset)) return lzs::kFallback;
-                lp += n; rem -= n;
+            while (rem > lzs::kMaxLitPiece) {
+                if (C.n_rec + 3 > row) return lzs::kRowFull;           // the pieces already recorded are written again by the step decoder: same bytes
+                if (!C.emit(lp, (uint32_t) lzs::kMaxLitPiece, 0, lzs::kNoOffset)) return lzs::kFallback;
+                lp += lzs::kMaxLitPiece; rem -= lzs::kMaxLitPiece;
             }
-            if (!C.emit(mpos, 0, ml, off)) return lzs::kFallback;
+            p = lp; ll = (uint32_t) rem;
         }
-        else if (!C.emit(p, ll, ml, off)) return lzs::kFallback;
+        // one record, or (long literal run) a literal-only record and the match on its own
+        if (!C.emit2(p, ll, ml, off, lx, mpos)) return lzs::kFallback;
         P.ip = p2;
         P.op = mop + (int32_t) ml;
         return lzs::kMore;

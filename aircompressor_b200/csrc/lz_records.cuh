@@ -120,6 +120,19 @@ struct ParseCtx {
         prev_lit_end = lit_pos + (int32_t) ll;
         return true;
     }
+    // A sequence as one record {ll, ml, off}, or -- split -- as a literal-only record {ll} and a match record {ml, off} whose
+    // (empty) literals sit at match_pos.  Written without a branch on `split`: the second slot is simply not counted when
+    // it is not needed (the row has room for two: the callers check n_rec + 2 <= row).
+    __device__ __forceinline__ bool emit2(int32_t lit_pos, uint32_t ll, uint32_t ml, uint32_t off, bool split, int32_t match_pos)
+    {
+        const int32_t skip = lit_pos - prev_lit_end;
+        if (skip > kMaxSkip || ml > kMaxMatch || off > kMaxOffset || ll > (uint32_t) kMaxLitPiece || match_pos - lit_pos - (int32_t) ll > kMaxSkip) return false;
+        rec[n_rec] = make_uint2(ll | (split ? 0u : ml << 12), (split ? kNoOffset : off) | ((uint32_t) skip << 24));
+        rec[n_rec + 1] = make_uint2(ml << 12, off | ((uint32_t) (match_pos - lit_pos - (int32_t) ll) << 24));
+        n_rec += split ? 2 : 1;
+        prev_lit_end = split ? match_pos : lit_pos + (int32_t) ll;
+        return true;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------------------
