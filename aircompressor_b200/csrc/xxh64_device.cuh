@@ -41,23 +41,38 @@ __device__ __forceinline__ uint64_t xxh64_group4(const uint8_t *in, int64_t len,
             for (; s < stripes; s++) v = mix(v, q[s * 4]);
         }
         else {
-            // any other alignment (blocks packed behind a ragged one): aligned 8-byte words, each value assembled from two of
-            // them -- the same number of independent loads in flight as the aligned loop instead of a chain of 4-byte loads
+            // any other alignment (blocks packed behind a ragged one): every lane loads ONE aligned 8-byte word per stripe
+            // (lane `sub` the word that holds the low part of its value); the high part is the word of the next lane of the
+            // group -- for the last lane the first word of the NEXT stripe, which lane 0 has already loaded one iteration
+            // ahead.  Same global traffic and the same number of loads as the aligned loop, two shuffles per value on top.
             const uintptr_t a = (uintptr_t) p;
             const uint32_t sh = (uint32_t) (a & 7) * 8;                 // != 0 here
             const uint64_t *q = (const uint64_t *) (a & ~(uintptr_t) 7);
+            const int lane = lane_id();
+            const int nb = (lane & ~3) | ((sub + 1) & 3);                // the neighbour that holds my high part
+            uint64_t w0 = q[0];
             int64_t s = 0;
-            for (; s + 4 <= stripes; s += 4) {
-                const uint64_t l0 = q[(s + 0) * 4], h0 = q[(s + 0) * 4 + 1], l1 = q[(s + 1) * 4], h1 = q[(s + 1) * 4 + 1];
-                const uint64_t l2 = q[(s + 2) * 4], h2 = q[(s + 2) * 4 + 1], l3 = q[(s + 3) * 4], h3 = q[(s + 3) * 4 + 1];
-                v = mix(v, (l0 >> sh) | (h0 << (64 - sh))); v = mix(v, (l1 >> sh) | (h1 << (64 - sh)));
-                v = mix(v, (l2 >> sh) | (h2 << (64 - sh))); v = mix(v, (l3 >> sh) | (h3 << (64 - sh)));
+            for (; s + 4 <= stripes; s += 4) {                          // four loads in flight per lane, like the aligned loop
+                const uint64_t w1 = q[(s + 1) * 4], w2 = q[(s + 2) * 4], w3 = q[(s + 3) * 4];
+                // behind the last stripe only lane 0's word is needed (it holds the last byte of lane 3's value, so it is inside
+                // the buffer's aligned extent); the other lanes do not read there
+                const uint64_t w4 = (s + 4 < stripes || sub == 0) ? q[(s + 4) * 4] : 0;
+                const uint64_t c0 = __shfl_sync(gmask, w0, nb), c1 = __shfl_sync(gmask, w1, nb), c2 = __shfl_sync(gmask, w2, nb),
+                               c3 = __shfl_sync(gmask, w3, nb), c4 = __shfl_sync(gmask, w4, nb);
+                const uint64_t h0 = sub == 3 ? c1 : c0, h1 = sub == 3 ? c2 : c1, h2 = sub == 3 ? c3 : c2, h3 = sub == 3 ? c4 : c3;
+                v = mix(v, (w0 >> sh) | (h0 << (64 - sh))); v = mix(v, (w1 >> sh) | (h1 << (64 - sh)));
+                v = mix(v, (w2 >> sh) | (h2 << (64 - sh))); v = mix(v, (w3 >> sh) | (h3 << (64 - sh)));
+                w0 = w4;
             }
-            for (; s < stripes; s++) v = mix(v, (q[s * 4] >> sh) | (q[s * 4 + 1] << (64 - sh)));
+            for (; s < stripes; s++) {
+                const uint64_t nxt = (s + 1 < stripes || sub == 0) ? q[(s + 1) * 4] : 0;
+                const uint64_t from_cur = __shfl_sync(gmask, w0, nb), from_nxt = __shfl_sync(gmask, nxt, nb);
+                v = mix(v, (w0 >> sh) | ((sub == 3 ? from_nxt : from_cur) << (64 - sh)));
+                w0 = nxt;
+            }
         }
         // gather the four accumulators of the group
-        const int lane = lane_id();
-        const int g0 = lane & ~3;
+        const int g0 = lane_id() & ~3;
         uint64_t v1 = __shfl_sync(gmask, v, g0 + 0);
         uint64_t v2 = __shfl_sync(gmask, v, g0 + 1);
         uint64_t v3 = __shfl_sync(gmask, v, g0 + 2);
