@@ -24,10 +24,18 @@ constexpr int kSeqBatch = 32;
 // warps per SM instead of 12 (the kernel is latency bound: lane 0 walks the FSE states alone).  Tables that a later
 // block or frame of the same input may reuse (treeless literals, repeat-mode sequence tables) are parked in the
 // warp's global scratch (kHufSave / kFseSave) whenever more input follows the current block.
+constexpr int kRing = 2048, kRingMask = kRing - 1;   // output ring of the sequence executor (bytes)
+constexpr int kFlush = 512;                          // the ring drains in pieces of at least this many bytes
+constexpr int32_t kFastMinBits = 256;                // the wide sequence path needs this many unread bits in front of a sequence
+
 struct WarpSmem {
     union {
         uint16_t huf[4096];   // symbol | nbits << 8
-        struct { uint32_t ll[512], ml[512], of[256]; };
+        struct {
+            uint32_t ll[512], ml[512], of[256];   // new_state (11) | extra bits of the code (5) << 11 | nbits (8) << 16 | symbol (8) << 24
+            uint8_t ring[kRing];                  // the newest output bytes of the block being executed (16-byte aligned: offset 5120)
+            uint32_t seq_p[kSeqBatch], seq_c[kSeqBatch];   // per sequence of a batch: unread bits in front of it, its three codes
+        };
     };
     uint32_t wt[64];          // FSE table of the Huffman weights (must not clobber ll/ml/of: repeat mode reuses them)
     int16_t norm[256];
@@ -41,6 +49,12 @@ struct Ctl {   // lane-0 results broadcast through registers
     int32_t reason;
     int64_t err_off;
 };
+
+#ifndef LZS_EMU
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+#else
+__device__ __forceinline__ void prefetch_l1(const void *) {}
+#endif
 
 #define ZFAIL(reason_, off_) do { ctl.reason = (reason_); ctl.err_off = (off_); return -1; } while (0)
 #define ZCHECK(cond, off_, reason_) do { if (!(cond)) ZFAIL(reason_, off_); } while (0)
@@ -291,6 +305,74 @@ __device__ __forceinline__ void copy_literals(uint8_t *dst, const Literals &lit,
     }
 }
 
+// ---- the wide sequence path: output ring -------------------------------------------------------------------------------
+// Positions are 32-bit and relative to the block: output position inside the block + (address of its first output byte & 15),
+// so that ring units and global 16-byte units are aligned alike; `out_al` is the (16-byte aligned) address of position 0.  A
+// match source in front of the block has a negative position.  `ring_lo` is the first position the ring holds.
+
+// moves [flushed, e) from the ring to global memory: 16-byte stores for whole aligned units, bytes for the partial units at both ends
+__device__ __forceinline__ void ring_flush(const uint8_t *ring, uint8_t *out_al, int32_t &flushed, const int32_t e, const int lane)
+{
+    int32_t a = flushed;
+    if (a & 15) {
+        int32_t a1 = (a + 15) & ~15;
+        if (a1 > e) a1 = e;
+        if (a + lane < a1) out_al[a + lane] = ring[(a + lane) & kRingMask];
+        a = a1;
+    }
+    const int32_t units = (e - a) >> 4;
+    for (int32_t u = lane; u < units; u += 32) {
+        const int32_t w = a + (u << 4);
+        *reinterpret_cast<uint4 *>(out_al + w) = *reinterpret_cast<const uint4 *>(ring + (w & kRingMask));
+    }
+    a += units << 4;
+    if (a + lane < e) out_al[a + lane] = ring[(a + lane) & kRingMask];
+    flushed = e;
+    __syncwarp();
+}
+
+// one sequence the multi-sequence step cannot take (more than 64 bytes, or a match that overlaps its own output): its literals,
+// then the match, in pieces of at most kFlush bytes so that the ring can drain in between
+__device__ __forceinline__ void ring_long_sequence(uint8_t *ring, const uint8_t *lit, uint8_t *out_al, int32_t &flushed, const int32_t ring_lo,
+                                                   const int32_t opw, const int32_t ll, const int32_t ml, const int32_t off, const int lane)
+{
+    for (int32_t cb = 0; cb < ll; cb += kFlush) {
+        const int32_t pn = ll - cb < kFlush ? ll - cb : kFlush;
+        for (int32_t i = lane; i < pn; i += 32) ring[(opw + cb + i) & kRingMask] = lit[cb + i];
+        __syncwarp();
+        if (opw + cb + pn - flushed >= kFlush) ring_flush(ring, out_al, flushed, (opw + cb + pn) & ~15, lane);
+    }
+    const int32_t mopw = opw + ll;
+    for (int32_t cb = 0; cb < ml; cb += kFlush) {
+        const int32_t pw = mopw + cb;                                   // first byte of this piece
+        const int32_t pn = ml - cb < kFlush ? ml - cb : kFlush;
+        if (off >= 32) {
+            for (int32_t base = 0; base < pn; base += 32) {             // a round only reads bytes written at least 32 positions earlier
+                const int32_t i = base + lane;
+                if (i < pn) {
+                    const int32_t pos = pw + i, src = pos - off;
+                    const int32_t lo = pw + base + 32 - kRing > ring_lo ? pw + base + 32 - kRing : ring_lo;
+                    ring[pos & kRingMask] = src >= lo ? ring[src & kRingMask] : out_al[src];   // older than the ring: flushed long ago
+                }
+                __syncwarp();
+            }
+        }
+        else {
+            // periodic pattern: every byte of the piece repeats one of the `off` bytes in front of it
+            int32_t m = lane % off;
+            const int32_t step = 32 % off;
+            for (int32_t i = lane; i < pn; i += 32) {
+                const int32_t src = pw - off + m;
+                ring[(pw + i) & kRingMask] = src >= ring_lo ? ring[src & kRingMask] : out_al[src];
+                m += step;
+                if (m >= off) m -= off;
+            }
+            __syncwarp();
+        }
+        if (pw + pn - flushed >= kFlush) ring_flush(ring, out_al, flushed, (pw + pn) & ~15, lane);
+    }
+}
+
 // decodes one compressed block (ZstdFrameDecompressor.decodeCompressedBlock :265-310 + decompressSequences :312-516).
 // Returns bytes produced or -1.  `out`/`out_pos` are relative to the start of the caller's output buffer.
 // copies n_bytes (a multiple of 16) between 16-byte aligned buffers with the whole warp
@@ -482,6 +564,18 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
         fs.of_log = __shfl_sync(kFull, lg[1], 0);
         fs.ml_log = __shfl_sync(kFull, lg[2], 0);
         __syncwarp();
+        // the number of extra bits of every code goes into its table entries (bits 11-15): the state walk of the wide path
+        // then needs no second lookup.  Tables brought back from the parking area already carry them.
+        for (int k = 0; k < 3; k++) {
+            if (((type >> (6 - 2 * k)) & 3) == 3) continue;
+            uint32_t *tab = k == 0 ? sm.ll : k == 1 ? sm.of : sm.ml;
+            const int size = 1 << (k == 0 ? fs.ll_log : k == 1 ? fs.of_log : fs.ml_log);
+            for (int i = lane; i < size; i += 32) {
+                const uint32_t e = tab[i], sym = e >> 24;
+                tab[i] = e | ((k == 0 ? (uint32_t) kLLBits[sym] : k == 1 ? sym : (uint32_t) kMLBits[sym]) << 11);
+            }
+        }
+        __syncwarp();
         if (keep_tables) warp_copy16(lit_scratch + kFseSave, sm.ll, kFseBytes, lane);
 
         // lane 0 owns the bit reader and the three FSE states; sequences are produced in batches of 32 and
@@ -504,7 +598,203 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
 
         int32_t remaining = seq_count;
         bool stop = false;   // overflow with sequenceCount == 0 -> leave the loop (Java `break`)
+
+        // ---- the wide path (every block whose literals are not a single repeated byte, as long as the bit stream is not
+        // about to run out).  Per batch of 32 sequences:
+        //   lane 0     walks the three FSE states only: table entry -> bits consumed -> next state, and notes where each
+        //              sequence's bits begin (no length or offset is assembled on the serial chain; the next window of the
+        //              stream is requested before it is needed);
+        //   all lanes  pull the extra bits of THEIR sequence out of the stream, resolve the repeated-offset codes in order,
+        //              find output / literal positions with two prefix sums, check the three conditions the Java checks per
+        //              sequence, and execute in STEPS of up to 64 output bytes covering as many consecutive sequences as
+        //              end inside them and copy from in front of the step.  Output is built in a 2 KiB shared-memory ring
+        //              (what a warp has just written is not in L1) and leaves it in 16-byte stores.
+        // While more than kFastMinBits unread bits lie in front of a sequence no refill rule of BitInputStream can trigger, so
+        // plain "bits in order" is what the Java reads; nearer to the start of the stream the exact loop below takes over.
+        bool wide = lit.rle < 0;
+        const int64_t abs0 = output;                                     // output position of ring position `oh`
+        const int32_t oh = (int32_t) ((uintptr_t) (out + abs0) & 15);
+        uint8_t *const out_al = out + abs0 - oh;
+        const int32_t ring_lo = oh;
+        int32_t opw = oh, flushed = oh;
+        const uint8_t *const bs = in + input;                            // first byte of the sequence bit stream
+        int32_t P = 0, wb = 0;                                           // lane 0: unread bits; byte position of the window
+        uint64_t w = 0;
+        bool b_stale = false;                                            // lane 0: `b` is behind P
+        if (lane == 0) P = (int32_t) (b.cur - b.start) * 8 + 64 - b.consumed;
+        const uint32_t le_mask = 0xffffffffu >> (31 - lane);             // lanes <= mine
+
         while (remaining > 0 && !stop) {
+            if (wide) {
+                int produced = 0;
+                if (lane == 0) {
+                    if (P >= kFastMinBits) {
+                        wb = (P - 57) >> 3;                               // window = bytes [wb, wb + 8): its top is 0..7 bits above P
+                        w = ld64u(bs + wb);
+                        if (wb >= 384) prefetch_l1(bs + wb - 384);        // the stream is read downwards: ask for the lines of the next batches
+                    }
+                    while (produced < kSeqBatch && remaining > 0 && P >= kFastMinBits) {
+                        const uint32_t el = sm.ll[ll_state], em = sm.ml[ml_state], eo = sm.of[of_state];
+                        sm.seq_p[produced] = (uint32_t) P;
+                        sm.seq_c[produced] = (el >> 24) | ((em >> 24) << 8) | ((eo >> 24) << 16);
+                        const int32_t P1 = P - (int32_t) (((el >> 11) & 31) + ((em >> 11) & 31) + ((eo >> 11) & 31));   // behind the extra bits
+                        int32_t sft = P1 - wb * 8;                        // the state bits are bits [sft - 26, sft) of the window
+                        if (sft < 32) { wb = (P1 - 57) >> 3; w = ld64u(bs + wb); sft = P1 - wb * 8; }
+                        uint32_t x = __funnelshift_rc((uint32_t) w, (uint32_t) (w >> 32), (uint32_t) (sft - 32));     // bits [sft - 32, sft)
+                        const uint32_t nbl = (el >> 16) & 15, nbm = (em >> 16) & 15, nbo = (eo >> 16) & 15;
+                        ll_state = (int) ((el & 0x7FF) + __funnelshift_lc(x, 0, nbl)); x <<= nbl;
+                        ml_state = (int) ((em & 0x7FF) + __funnelshift_lc(x, 0, nbm)); x <<= nbm;
+                        of_state = (int) ((eo & 0x7FF) + __funnelshift_lc(x, 0, nbo));
+                        P = P1 - (int32_t) (nbl + nbm + nbo);
+                        wb = (P - 57) >> 3;                               // next window, requested now, needed one table lookup later
+                        w = ld64u(bs + wb);
+                        produced++;
+                        remaining--;
+                        b_stale = true;
+                    }
+                }
+#ifdef LZS_EMU
+                if (lane == 0) emu_count_wide(produced);
+#endif
+                produced = __shfl_sync(kFull, produced, 0);
+                remaining = __shfl_sync(kFull, remaining, 0);
+                const bool leave = remaining > 0 && produced < kSeqBatch;   // close to the start of the stream: the exact loop takes over
+                __syncwarp();
+                if (produced) {
+                    // ---- every lane: the lengths and the offset code of ITS sequence
+                    int32_t my_ll = 0, my_ml = 0;
+                    uint32_t my_key = 0;                                  // a new offset, or 0x80000000 | repeated-offset code 0..3
+                    if (lane < produced) {
+                        const int32_t ps = (int32_t) sm.seq_p[lane];
+                        const uint32_t c = sm.seq_c[lane];
+                        const uint32_t llc = c & 0xFF, mlc = (c >> 8) & 0xFF, ofc = c >> 16;
+                        int32_t a = (ps - 57) >> 3;
+                        uint64_t v = ld64u(bs + a) << (64 - (ps - a * 8));   // the next unread bit is bit 63
+                        const uint32_t ofx = (uint32_t) ((v >> 1) >> (63 - ofc));
+                        const int32_t q = ps - (int32_t) ofc;
+                        const uint32_t mlb = kMLBits[mlc], llb = kLLBits[llc];
+                        a = (q - 57) >> 3;
+                        v = ld64u(bs + a) << (64 - (q - a * 8));
+                        const uint32_t mlx = (uint32_t) ((v >> 1) >> (63 - mlb));
+                        v <<= mlb;
+                        const uint32_t llx = (uint32_t) ((v >> 1) >> (63 - llb));
+                        my_ml = kMLBase[mlc] + (int32_t) mlx;
+                        my_ll = kLLBase[llc] + (int32_t) llx;
+                        const uint32_t ofv = (uint32_t) of_base((int) ofc) + ofx;
+                        my_key = ofc <= 1 ? (0x80000000u | (ofv + (llc == 0 ? 1u : 0u))) : ofv;
+                    }
+                    // ---- repeated offsets, in sequence order (:380-408); every lane keeps the history, lane s keeps offset s
+                    int32_t my_off = 0;
+                    for (int s = 0; s < produced; s++) {
+                        const uint32_t k = __shfl_sync(kFull, my_key, s);
+                        if (k & 0x80000000u) {
+                            const uint32_t o = k & 3;
+                            if (o != 0) {
+                                int32_t temp = o == 3 ? p0 - 1 : (o == 1 ? p1 : p2);
+                                if (temp == 0) temp = 1;
+                                if (o != 1) p2 = p1;
+                                p1 = p0;
+                                p0 = temp;
+                            }
+                        }
+                        else { p2 = p1; p1 = p0; p0 = (int32_t) k; }
+                        if (lane == s) my_off = p0;
+                    }
+                    // ---- positions: prefix sums over the batch
+                    const int32_t my_total = my_ll + my_ml;
+                    int32_t a = my_ll, t = my_total;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int32_t ua = __shfl_up_sync(kFull, a, o), ut = __shfl_up_sync(kFull, t, o);
+                        if (lane >= o) { a += ua; t += ut; }
+                    }
+                    const int32_t my_opw = opw + t - my_total;            // where my output starts
+                    const int32_t my_mop = my_opw + my_ll;                // ... and where my match starts
+                    const int32_t my_dl = (a - my_ll) - my_opw;           // literal index in the batch = output position + my_dl
+                    // ---- the three checks of the Java loop, first failing sequence first
+                    int bad = 0;
+                    if (lane < produced) {
+                        if (abs0 + (my_opw - oh) + my_total > out_cap) bad = R_OUTPUT_TOO_SMALL;
+                        else if (lit_pos + a > lit.size) bad = R_CORRUPTED;
+                        else if (abs0 + (my_mop - oh) - my_off < 0) bad = R_CORRUPTED;
+                    }
+                    const unsigned badm = __ballot_sync(kFull, bad != 0);
+                    if (badm) ZFAIL(__shfl_sync(kFull, bad, __ffs((int) badm) - 1), input);
+                    const uint8_t *const litb = lit.ptr + lit_pos;
+                    if (lane < produced) {                                // ask for the lines now: the steps below then find them in L1
+                        if (my_ll) prefetch_l1(litb + (a - my_ll));
+                        if (my_mop - my_off < my_mop + my_ml - kRing) prefetch_l1(out_al + (my_mop - my_off));
+                    }
+                    int f = 0;
+                    while (f < produced) {
+                        // ---- a step: as many consecutive sequences as end within 64 bytes of the first one's start S and take all
+                        // their match bytes from in front of S (then no byte of the step depends on another byte of the step)
+                        const int32_t S = __shfl_sync(kFull, my_opw, f);
+                        const int32_t endk = my_opw + my_total - S;
+                        const bool fits = lane >= f && lane < produced && endk <= 64 && my_off >= endk;
+                        const uint32_t run = __ballot_sync(kFull, fits) >> f;
+                        const int nfit = __ffs((int) ~run) - 1;           // a sequence has at least 3 bytes: never 32 of them in a step
+                        if (nfit == 0) {
+                            ring_long_sequence(sm.ring, litb + __shfl_sync(kFull, a - my_ll, f), out_al, flushed, ring_lo, S,
+                                               __shfl_sync(kFull, my_ll, f), __shfl_sync(kFull, my_ml, f), __shfl_sync(kFull, my_off, f), lane);
+                            f++;
+                            continue;
+                        }
+                        const int32_t E = __shfl_sync(kFull, endk, f + nfit - 1);   // bytes of this step
+                        const int32_t rlo = S + E - kRing > ring_lo ? S + E - kRing : ring_lo;   // oldest position the ring still holds
+                        // which sequence produces byte j of the step: count the sequence starts at or below j
+                        const bool inwin = lane >= f && lane < f + nfit;
+                        const int32_t st = my_opw - S;
+                        const uint32_t lo = __reduce_or_sync(kFull, (inwin && st < 32) ? 1u << st : 0u);
+                        {
+                            const int r = f - 1 + __popc(lo & le_mask);
+                            const int32_t mop = __shfl_sync(kFull, my_mop, r), dl = __shfl_sync(kFull, my_dl, r), off = __shfl_sync(kFull, my_off, r);
+                            const int32_t pos = S + lane;
+                            if (lane < E) {
+                                uint8_t v;
+                                if (pos < mop) v = litb[pos + dl];
+                                else {
+                                    const int32_t src = pos - off;
+                                    v = src >= rlo ? sm.ring[src & kRingMask] : out_al[src];
+                                }
+                                sm.ring[pos & kRingMask] = v;
+                            }
+                        }
+                        if (E > 32) {
+                            const uint32_t hi = __reduce_or_sync(kFull, (inwin && st >= 32) ? 1u << (st - 32) : 0u);
+                            const int r = f - 1 + __popc(lo) + __popc(hi & le_mask);
+                            const int32_t mop = __shfl_sync(kFull, my_mop, r), dl = __shfl_sync(kFull, my_dl, r), off = __shfl_sync(kFull, my_off, r);
+                            const int32_t pos = S + 32 + lane;
+                            if (lane + 32 < E) {
+                                uint8_t v;
+                                if (pos < mop) v = litb[pos + dl];
+                                else {
+                                    const int32_t src = pos - off;
+                                    v = src >= rlo ? sm.ring[src & kRingMask] : out_al[src];
+                                }
+                                sm.ring[pos & kRingMask] = v;
+                            }
+                        }
+                        __syncwarp();
+                        f += nfit;
+                        if (S + E - flushed >= kFlush) ring_flush(sm.ring, out_al, flushed, (S + E) & ~15, lane);
+                    }
+                    lit_pos += __shfl_sync(kFull, a, 31);
+                    opw += __shfl_sync(kFull, t, 31);
+                    output = abs0 + (opw - oh);
+                }
+                if (leave) {
+                    if (opw != flushed) ring_flush(sm.ring, out_al, flushed, opw, lane);
+                    wide = false;
+                    if (lane == 0 && b_stale) {                           // the state BitInputStream.load() is in at this point
+                        const int32_t cr = (P - 57) >> 3;
+                        b.cur = b.start + cr;
+                        b.consumed = cr * 8 + 64 - P;
+                        b.bits = ld64u(b.in + b.cur);
+                        b.overflow = 0;
+                    }
+                }
+                continue;
+            }
             int produced = 0;
             int fail = 0;
             if (lane == 0) {
@@ -544,15 +834,18 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
                     if (ll_code > 15) { lit_length += (int32_t) peek_bits(b.consumed, b.bits, ll_bits); b.consumed += ll_bits; }
                     if (ll_bits + ml_bits + of_bits > 64 - 7 - (9 + 9 + 8)) br_load(b);
                     int nb;
-                    nb = (el >> 16) & 0xFF; ll_state = (int) ((el & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
-                    nb = (em >> 16) & 0xFF; ml_state = (int) ((em & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
-                    nb = (eof >> 16) & 0xFF; of_state = (int) ((eof & 0xFFFF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (el >> 16) & 0xFF; ll_state = (int) ((el & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (em >> 16) & 0xFF; ml_state = (int) ((em & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (eof >> 16) & 0xFF; of_state = (int) ((eof & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
                     sm.seq_ll[produced] = lit_length;
                     sm.seq_ml[produced] = match_length;
                     sm.seq_of[produced] = offset;
                     produced++;
                 }
             }
+#ifdef LZS_EMU
+            if (lane == 0) emu_count_exact(produced);
+#endif
             produced = __shfl_sync(kFull, produced, 0);
             fail = __shfl_sync(kFull, fail, 0);
             remaining = __shfl_sync(kFull, remaining, 0);
@@ -571,8 +864,8 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
                 if (lane < produced) {
                     const int64_t lp = lit_pos + (a - my_ll);                       // literal position of sequence `lane`
                     const int64_t ms = output + (t - sm.seq_ml[lane]) - sm.seq_of[lane];   // its match source
-                    if (lit.rle < 0 && my_ll > 0 && lp < lit.size) asm volatile("prefetch.global.L1 [%0];" :: "l"(lit.ptr + lp));
-                    if (ms >= 0 && ms < output) asm volatile("prefetch.global.L1 [%0];" :: "l"(out + ms));
+                    if (lit.rle < 0 && my_ll > 0 && lp < lit.size) prefetch_l1(lit.ptr + lp);
+                    if (ms >= 0 && ms < output) prefetch_l1(out + ms);
                 }
             }
             // execute (all lanes, in order)
@@ -605,6 +898,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
             if (fail) ZFAIL(fail, input);
             __syncwarp();
         }
+        if (wide && opw != flushed) ring_flush(sm.ring, out_al, flushed, opw, lane);   // the block ended on the wide path
         fs.prev[0] = __shfl_sync(kFull, p0, 0);
         fs.prev[1] = __shfl_sync(kFull, p1, 0);
         fs.prev[2] = __shfl_sync(kFull, p2, 0);
@@ -697,7 +991,11 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
 
         if (has_checksum) {
             __syncwarp();
+#ifndef LZS_EMU
             const uint64_t hash = xxh64_group4(out + output_start, lane < 4 ? output - output_start : 0, 0, lane & 3, 0xFu << (lane & ~3));
+#else
+            const uint64_t hash = emu_xxh64(out + output_start, output - output_start);   // host emulation: scalar, no group shuffles
+#endif
             const uint32_t h32 = (uint32_t) __shfl_sync(kFull, hash, 0);
             ZCHECK(input + 4 <= in_len, input, R_NOT_ENOUGH_INPUT);
             if (ld32u(in + input) != h32) ZFAIL(R_BAD_CHECKSUM, input);
@@ -707,6 +1005,7 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
     return output;
 }
 
+#ifndef LZS_EMU
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
 {
     extern __shared__ __align__(16) uint8_t zsmem[];
@@ -730,6 +1029,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) zstd_decompress_kernel(A
     }
 }
 
+#endif  // LZS_EMU
 }  // namespace
 
 static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256 + kHufBytes + kFseBytes;   // literals | parked Huffman table | parked FSE tables
@@ -738,6 +1038,7 @@ int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * 5; }   // 
 
 int64_t acc_zstd_dec_scratch_bytes(int sm_count) { return acc_zstd_dec_grid(sm_count) * kWarpsPerCta * kZstdDecScratchPerWarp; }
 
+#ifndef LZS_EMU
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes)
 {
     const int smem = kWarpsPerCta * (int) sizeof(WarpSmem);
@@ -749,3 +1050,4 @@ void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st
     (void) scratch_bytes;
     zstd_decompress_kernel<<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
 }
+#endif  // LZS_EMU

@@ -47,9 +47,7 @@ static inline unsigned long long emu_xchg(unsigned long long v, int src)
     __syncwarp();
     return r;
 }
-static inline unsigned long long __shfl_sync(unsigned, unsigned long long v, int src) { return emu_xchg(v, src); }
-static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return (uint32_t) emu_xchg(v, src); }
-static inline int __shfl_sync(unsigned, int v, int src) { return (int) emu_xchg((unsigned long long) (long long) v, src); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return (T) emu_xchg((unsigned long long) (long long) v, src); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned delta) { const int src = t_lane - (int) delta; return (T) emu_xchg((unsigned long long) v, src < 0 ? t_lane : src); }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned delta) { const int src = t_lane + (int) delta; return (T) emu_xchg((unsigned long long) v, src > 31 ? t_lane : src); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return (T) emu_xchg((unsigned long long) v, t_lane ^ m); }
@@ -78,4 +76,7 @@ static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 [[noreturn]] static inline void emu_unsupported(const char *what) { fprintf(stderr, "cuda_emu: %s reached\n", what); abort(); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *) p; }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh > 32 ? 32 : sh)); }
+static inline uint32_t __funnelshift_lc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) ((((((uint64_t) hi) << 32) | lo) << (sh > 32 ? 32 : sh)) >> 32); }
+static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh & 31)); }
