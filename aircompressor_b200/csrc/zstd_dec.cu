@@ -266,18 +266,44 @@ __device__ int64_t huf_read_table(WarpSmem &sm, FrameState &fs, const uint8_t *i
     return ret;
 }
 
-// One Huffman stream decoded by one thread (Huffman.decodeTail semantics, zstd/Huffman.java:291-317).
+// One Huffman stream decoded by one thread (Huffman.decodeTail semantics, zstd/Huffman.java:291-317).  Away from the start
+// of the stream a refill is BitInputStream.load() on its common path (at least 57 unread bits afterwards), which four symbols
+// of at most 12 bits cannot exhaust: the main loop decodes four symbols per refill from a top-aligned copy of the word and
+// writes them with one 32-bit store.  The last bytes of the stream and of the output go through the symbol-by-symbol loops.
 __device__ int huf_decode_stream(const uint16_t *huf, int tl, const uint8_t *in, int64_t start, int64_t end, uint8_t *out, int64_t n, int64_t *err_off)
 {
     BitReader b;
     int r = br_init(b, in, start, end, err_off);
     if (r) return r;
     int64_t o = 0;
-    while (o < n) {
-        if (br_load(b)) break;
+    bool at_start = false;
+    while (o < n && ((uintptr_t) (out + o) & 3)) {           // up to the first 4-byte aligned output address
+        if (br_load(b)) { at_start = true; break; }
         uint32_t e = huf[(int) peek_bits_fast(b.consumed, b.bits, tl)];
         out[o++] = (uint8_t) e;
         b.consumed += e >> 8;
+    }
+    if (!at_start) {
+        const int sh = 64 - tl;
+        while (o + 4 <= n && b.cur >= b.start + 8) {
+            b.cur -= b.consumed >> 3;
+            b.consumed &= 7;
+            b.bits = ld64u(b.in + b.cur);
+            uint64_t v = b.bits << b.consumed;
+            const uint32_t e0 = huf[(uint32_t) (v >> sh)]; v <<= e0 >> 8;
+            const uint32_t e1 = huf[(uint32_t) (v >> sh)]; v <<= e1 >> 8;
+            const uint32_t e2 = huf[(uint32_t) (v >> sh)]; v <<= e2 >> 8;
+            const uint32_t e3 = huf[(uint32_t) (v >> sh)];
+            b.consumed += (int32_t) ((e0 >> 8) + (e1 >> 8) + (e2 >> 8) + (e3 >> 8));
+            *reinterpret_cast<uint32_t *>(out + o) = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | (e3 << 24);
+            o += 4;
+        }
+        while (o < n) {
+            if (br_load(b)) break;
+            uint32_t e = huf[(int) peek_bits_fast(b.consumed, b.bits, tl)];
+            out[o++] = (uint8_t) e;
+            b.consumed += e >> 8;
+        }
     }
     while (o < n) {
         uint32_t e = huf[(int) peek_bits_fast(b.consumed, b.bits, tl)];
