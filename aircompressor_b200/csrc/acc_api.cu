@@ -293,7 +293,7 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
             int64_t need = zstd_scratch_bytes(op, b.n, c->sm_count);
             if (!grow(&c->d_scratch, &c->d_scratch_cap, need, false)) return -ACC_STATUS(ACC_E_CUDA, (int) cudaErrorMemoryAllocation);
             if (op == ACC_OP_ZSTD_COMPRESS) acc_launch_zstd_compress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);
-            else acc_launch_zstd_decompress(b, c->sm_count, st, c->d_scratch, c->d_scratch_cap);
+            else acc_launch_zstd_decompress(b, c->sm_count, c->tuning_ctas_per_sm, st, c->d_scratch, c->d_scratch_cap);
             break;
         }
         default: return -ACC_STATUS(ACC_E_ARGUMENT, 0);

@@ -18,32 +18,41 @@ using namespace zs;
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kSeqBatch = 32;
-
-// The Huffman table (needed while the literals of a block are decoded) and the three FSE tables (needed while its
-// sequences are decoded) share one 8 KiB region: 10.2 KiB of shared memory per warp instead of 15.2, i.e. 20 resident
-// warps per SM instead of 12 (the kernel is latency bound: lane 0 walks the FSE states alone).  Tables that a later
-// block or frame of the same input may reuse (treeless literals, repeat-mode sequence tables) are parked in the
-// warp's global scratch (kHufSave / kFseSave) whenever more input follows the current block.
 constexpr int kRing = 2048, kRingMask = kRing - 1;   // output ring of the sequence executor (bytes)
 constexpr int kFlush = 512;                          // the ring drains in pieces of at least this many bytes
 constexpr int32_t kFastMinBits = 256;                // the wide sequence path needs this many unread bits in front of a sequence
+constexpr int kHufSmemLog = 11;                      // Huffman tables up to this log live in shared memory
 
+// Shared memory of a warp, 7.4 KiB in three regions whose tenants are never live at the same time:
+//   A  the Huffman table while the literals of a block are decoded (2048 x u16: table logs up to 11, which is what the Java and
+//      libzstd encoders emit; a 12-bit table -- legal for the Java decoder -- lives in the warp's global scratch), then the
+//      three FSE tables while its sequences are decoded;
+//   B  table-building scratch (weights, normalized counts, the FSE table of the Huffman weights), then the output ring;
+//   C  the sequence batch of the wide path / of the exact loop.
+// Tables a later block or frame of the same input may reuse (treeless literals, repeat-mode sequence tables) are parked in the
+// warp's global scratch (kHufSave / kFseSave) whenever more input follows the current block.  The kernel is latency bound
+// (serial bit-stream walks), so resident warps per SM are what this layout buys: 28 instead of 20 with 10.2 KiB.
 struct WarpSmem {
     union {
-        uint16_t huf[4096];   // symbol | nbits << 8
+        uint16_t huf[2048];                       // symbol | nbits << 8
+        struct { uint32_t ll[512], ml[512], of[256]; };   // new_state (11) | extra bits of the code (5) << 11 | nbits (8) << 16 | symbol (8) << 24
+    };
+    union {
+        uint8_t ring[kRing];                      // the newest output bytes of the block being executed (16-byte aligned: offset 5120)
         struct {
-            uint32_t ll[512], ml[512], of[256];   // new_state (11) | extra bits of the code (5) << 11 | nbits (8) << 16 | symbol (8) << 24
-            uint8_t ring[kRing];                  // the newest output bytes of the block being executed (16-byte aligned: offset 5120)
-            uint32_t seq_p[kSeqBatch], seq_c[kSeqBatch];   // per sequence of a batch: unread bits in front of it, its three codes
+            uint32_t wt[64];                      // FSE table of the Huffman weights
+            int16_t norm[256];
+            int16_t next[256];
+            uint8_t scratch[512];                 // symbol spread buffer / Huffman weights
+            int32_t ranks[16];
         };
     };
-    uint32_t wt[64];          // FSE table of the Huffman weights (must not clobber ll/ml/of: repeat mode reuses them)
-    int16_t norm[256];
-    int16_t next[256];
-    uint8_t scratch[512];     // symbol spread buffer / Huffman weights
-    int32_t seq_ll[kSeqBatch], seq_ml[kSeqBatch], seq_of[kSeqBatch];
-    int32_t ranks[16];
+    union {
+        struct { uint32_t seq_p[kSeqBatch], seq_c[kSeqBatch]; };   // wide path, per sequence: unread bits in front of it, its three codes
+        struct { int32_t seq_ll[kSeqBatch], seq_ml[kSeqBatch], seq_of[kSeqBatch]; };   // exact loop
+    };
 };
+static_assert(sizeof(WarpSmem) == 5120 + kRing + 384 && sizeof(WarpSmem) % 16 == 0, "WarpSmem layout");
 
 struct Ctl {   // lane-0 results broadcast through registers
     int32_t reason;
@@ -178,7 +187,7 @@ struct FrameState {
 };
 
 // Huffman.readTable :52-128.  Lane 0 reads the weights, all lanes fill the table.  Returns bytes consumed or -1 (uniform).
-__device__ int64_t huf_read_table(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int size, Ctl &ctl, int lane)
+__device__ int64_t huf_read_table(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int size, uint16_t *big_table, Ctl &ctl, int lane)
 {
     uint8_t *weights = sm.scratch;   // 257 needed; scratch has 512
     int32_t *ranks = sm.ranks;
@@ -254,12 +263,13 @@ __device__ int64_t huf_read_table(WarpSmem &sm, FrameState &fs, const uint8_t *i
     table_log = __shfl_sync(kFull, table_log, 0);
     __syncwarp();
     // fill: symbol n covers [start, start + (1 << w) >> 1)
+    uint16_t *const tab = table_log > kHufSmemLog ? big_table : sm.huf;
     for (int n = 0; n < number_of_symbols; n++) {
         int w = weights[n];
         int length = (1 << w) >> 1;
         int start = (uint16_t) sm.norm[n];
         uint16_t e = (uint16_t) (n | ((table_log + 1 - w) << 8));
-        for (int i = lane; i < length; i += 32) sm.huf[start + i] = e;
+        for (int i = lane; i < length; i += 32) tab[start + i] = e;
     }
     __syncwarp();
     fs.huf_log = table_log;
@@ -471,23 +481,25 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
         ZCHECK(header_size + comp_size <= block_size, input, R_CORRUPTED);
         input += header_size;
         const int64_t lit_limit = input + comp_size;
+        uint16_t *const big_table = reinterpret_cast<uint16_t *>(lit_scratch + kHufSave);   // where a 12-bit table lives, and where smaller ones are parked
         if (lit_type != 3) {
-            int64_t used = huf_read_table(sm, fs, in, input, comp_size, ctl, lane);
+            int64_t used = huf_read_table(sm, fs, in, input, comp_size, big_table, ctl, lane);
             if (used < 0) return -1;
             input += used;
-            if (keep_tables) warp_copy16(lit_scratch + kHufSave, sm.huf, kHufBytes, lane);
+            if (keep_tables && fs.huf_log <= kHufSmemLog) warp_copy16(big_table, sm.huf, (int) sizeof(sm.huf), lane);
         }
-        else {
+        else if (fs.huf_log <= kHufSmemLog) {
             // treeless literals: the table of an earlier block (parked when it was built: something followed that block)
             __syncwarp();
-            warp_copy16(sm.huf, lit_scratch + kHufSave, kHufBytes, lane);
+            warp_copy16(sm.huf, big_table, (int) sizeof(sm.huf), lane);
         }
+        const uint16_t *const huf = fs.huf_log > kHufSmemLog ? big_table : sm.huf;
         // streams
         int reason = 0;
         int64_t eo = 0;
         const int tl = fs.huf_log;
         if (single) {
-            if (lane == 0) reason = huf_decode_stream(sm.huf, tl, in, input, lit_limit, lit_scratch, unc_size, &eo);
+            if (lane == 0) reason = huf_decode_stream(huf, tl, in, input, lit_limit, lit_scratch, unc_size, &eo);
         }
         else {
             // decode4Streams :166-289
@@ -503,7 +515,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
                     int64_t o0 = seg * lane;
                     int64_t n = lane < 3 ? seg : (int64_t) unc_size - 3 * seg;
                     if (n < 0) n = 0;   // tiny 4-stream sections: the Java decodes nothing from stream 4 but still wants it fully consumed
-                    reason = huf_decode_stream(sm.huf, tl, in, st, en, lit_scratch + o0, n, &eo);
+                    reason = huf_decode_stream(huf, tl, in, st, en, lit_scratch + o0, n, &eo);
                 }
             }
         }
@@ -1032,7 +1044,8 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
 }
 
 #ifndef LZS_EMU
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
+template <int kCtasPerSm>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) zstd_decompress_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
 {
     extern __shared__ __align__(16) uint8_t zsmem[];
     const int lane = lane_id();
@@ -1060,20 +1073,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) zstd_decompress_kernel(A
 
 static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256 + kHufBytes + kFseBytes;   // literals | parked Huffman table | parked FSE tables
 
-int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * 5; }   // 5 CTAs x 4 warps per SM (shared memory bound)
+constexpr int kZstdDecMaxCtasPerSm = 7, kZstdDecCtasPerSm = 5;   // shared memory allows 7 CTAs x 4 warps (30 KiB each); the scratch is sized for that
+
+int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * kZstdDecMaxCtasPerSm; }
 
 int64_t acc_zstd_dec_scratch_bytes(int sm_count) { return acc_zstd_dec_grid(sm_count) * kWarpsPerCta * kZstdDecScratchPerWarp; }
 
 #ifndef LZS_EMU
-void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes)
+template <int kCtasPerSm>
+static void launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch)
 {
     const int smem = kWarpsPerCta * (int) sizeof(WarpSmem);
-    cudaFuncSetAttribute(zstd_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(zstd_decompress_kernel<kCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int64_t ctas = (b.n + kWarpsPerCta - 1) / kWarpsPerCta;
-    int64_t max_ctas = acc_zstd_dec_grid(sm_count);
+    const int64_t max_ctas = (int64_t) sm_count * kCtasPerSm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
+    zstd_decompress_kernel<kCtasPerSm><<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
+}
+
+// ctas_per_sm: 0 = the default; 5, 6 or 7 = resident CTAs per SM the kernel is compiled for (96 / 80 / 72 registers per thread)
+void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, int64_t scratch_bytes)
+{
     (void) scratch_bytes;
-    zstd_decompress_kernel<<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
+    const int c = ctas_per_sm ? ctas_per_sm : kZstdDecCtasPerSm;
+    if (c <= 5) launch_zstd_decompress<5>(b, sm_count, st, scratch);
+    else if (c == 6) launch_zstd_decompress<6>(b, sm_count, st, scratch);
+    else launch_zstd_decompress<7>(b, sm_count, st, scratch);
 }
 #endif  // LZS_EMU
