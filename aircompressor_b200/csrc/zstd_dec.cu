@@ -22,6 +22,12 @@ constexpr int kRing = 2048, kRingMask = kRing - 1;   // output ring of the seque
 constexpr int kFlush = 512;                          // the ring drains in pieces of at least this many bytes
 constexpr int32_t kFastMinBits = 256;                // the wide sequence path needs this many unread bits in front of a sequence
 constexpr int kHufSmemLog = 11;                      // Huffman tables up to this log live in shared memory
+constexpr int kSlots = 2;                            // record batches a worker holds (the chain lane of the service kernel runs ahead)
+#ifndef LZS_EMU
+constexpr int kWorkers = 7;                          // service kernel: worker warps per CTA (+ one chain warp)
+#else
+constexpr int kWorkers = 2;
+#endif
 
 // Shared memory of a warp, 7.4 KiB in three regions whose tenants are never live at the same time:
 //   A  the Huffman table while the literals of a block are decoded (2048 x u16: table logs up to 11, which is what the Java and
@@ -48,11 +54,126 @@ struct WarpSmem {
         };
     };
     union {
-        struct { uint32_t seq_p[kSeqBatch], seq_c[kSeqBatch]; };   // wide path, per sequence: unread bits in front of it, its three codes
+        uint2 rec[kSlots][kSeqBatch];             // wide path, per sequence: {unread bits in front of it, its three codes}; two batches
         struct { int32_t seq_ll[kSeqBatch], seq_ml[kSeqBatch], seq_of[kSeqBatch]; };   // exact loop
     };
 };
-static_assert(sizeof(WarpSmem) == 5120 + kRing + 384 && sizeof(WarpSmem) % 16 == 0, "WarpSmem layout");
+static_assert(sizeof(WarpSmem) == 5120 + kRing + 512 && sizeof(WarpSmem) % 16 == 0, "WarpSmem layout");
+
+// ---- the FSE state walk ------------------------------------------------------------------------------------------------
+// One lane, one block: table entry -> bits consumed -> next state, noting where each sequence's bits begin.  Lengths and
+// offsets are NOT assembled here (the worker's lanes do that in parallel); the next window of the stream is requested before
+// it is needed.  Valid while at least kFastMinBits unread bits lie in front of a sequence.
+struct Chain {
+    const uint8_t *bs;        // first byte of the sequence bit stream
+    int32_t P, wb;            // unread bits; byte position of the window
+    uint64_t w;               // bytes [wb, wb + 8) of the stream
+    uint32_t sl, sm, so;      // the three states
+    __device__ __forceinline__ void open()
+    {
+        wb = (P - 57) >> 3;   // the window's top is 0..7 bits above P
+        w = ld64u(bs + wb);
+    }
+    __device__ __forceinline__ uint2 step(const uint32_t *ll, const uint32_t *ml, const uint32_t *of)
+    {
+        const uint32_t el = ll[sl], em = ml[sm], eo = of[so];
+        const uint2 r = make_uint2((uint32_t) P, (el >> 24) | ((em >> 24) << 8) | ((eo >> 24) << 16));
+        const int32_t P1 = P - (int32_t) (((el >> 11) & 31) + ((em >> 11) & 31) + ((eo >> 11) & 31));   // behind the extra bits
+        int32_t sft = P1 - wb * 8;                        // the state bits are bits [sft - 26, sft) of the window
+        if (sft < 32) { wb = (P1 - 57) >> 3; w = ld64u(bs + wb); sft = P1 - wb * 8; }
+        uint32_t x = __funnelshift_rc((uint32_t) w, (uint32_t) (w >> 32), (uint32_t) (sft - 32));     // bits [sft - 32, sft)
+        const uint32_t nbl = (el >> 16) & 15, nbm = (em >> 16) & 15, nbo = (eo >> 16) & 15;
+        sl = (el & 0x7FF) + __funnelshift_lc(x, 0, nbl); x <<= nbl;
+        sm = (em & 0x7FF) + __funnelshift_lc(x, 0, nbm); x <<= nbm;
+        so = (eo & 0x7FF) + __funnelshift_lc(x, 0, nbo);
+        P = P1 - (int32_t) (nbl + nbm + nbo);
+        wb = (P - 57) >> 3;                               // next window, requested now, needed one table lookup later
+        w = ld64u(bs + wb);
+        return r;
+    }
+};
+
+// ---- the state walk as a service ---------------------------------------------------------------------------------------
+// The kernel is bound by warp instructions (ALU pipe), and the state walk is a third of them with ONE lane working.  In the
+// service kernel a CTA is kWorkers worker warps + one chain warp whose lane w walks the states of worker w's block: one warp
+// instruction advances up to kWorkers blocks.  Worker and lane talk through a mailbox in shared memory: the worker posts
+// {stream, unread bits, states, sequence count}; the lane fills the worker's two record slots batch by batch (it runs ahead
+// by at most two batches) and ends with the state it stopped in -- at the last sequence, or kFastMinBits before the start of
+// the stream, where the worker's exact loop takes over.  A worker that gives up on a block (malformed input) simply posts its
+// next request: batches carry the request number and stale ones are dropped.
+struct ChainBox {
+    const uint8_t *bs;
+    int32_t P;
+    int32_t n;                // sequences wanted
+    uint32_t states;          // ll | ml << 10 | of << 20
+    uint32_t posted;          // requests posted by the worker
+    uint32_t consumed;        // batches the worker is done with
+    uint32_t produced;        // batches published by the chain lane
+    uint32_t count[kSlots];   // sequences of the batch | request number << 8 | kChainFinal
+    int32_t end_P;            // with the final batch: where the walk stopped
+    uint32_t end_states;
+};
+constexpr uint32_t kChainFinal = 0x80000000u;
+
+#ifndef LZS_EMU
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+__device__ __forceinline__ void pause_ns(unsigned ns) { __nanosleep(ns); }
+#else
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void pause_ns(unsigned) { sched_yield(); }
+#endif
+
+// the chain warp of a CTA: lane w serves worker w in rounds of one sequence per active lane
+__device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, const uint32_t *workers_done, const int lane)
+{
+    ChainBox *const box = boxes + (lane < kWorkers ? lane : 0);
+    const WarpSmem &sm = sms[lane < kWorkers ? lane : 0];
+    uint2 *const slots = const_cast<uint2 *>(&sm.rec[0][0]);
+    const bool serving = lane < kWorkers;
+    bool active = false;
+    uint32_t seen = 0, batches = 0, fill = 0;
+    int32_t n = 0;
+    Chain ch;
+    ch.bs = nullptr; ch.P = 0; ch.wb = 0; ch.w = 0; ch.sl = ch.sm = ch.so = 0;
+    for (;;) {
+        bool worked = false;
+        if (serving) {
+            const uint32_t posted = ld_vol(&box->posted);
+            if (posted != seen) {                          // a new request (also: the worker gave up on the previous one)
+                seen = posted;
+                __threadfence_block();
+                ch.bs = box->bs; ch.P = box->P; n = box->n;
+                const uint32_t st = box->states;
+                ch.sl = st & 1023; ch.sm = (st >> 10) & 1023; ch.so = st >> 20;
+                if (ch.P >= kFastMinBits) ch.open();
+                active = true;
+                fill = 0;
+            }
+            bool go = active;
+            if (go && fill == 0) go = batches - ld_vol(&box->consumed) < (uint32_t) kSlots;   // a free slot?
+            if (go) {
+                uint2 *const slot = slots + (batches & (kSlots - 1)) * kSeqBatch;
+                if (ch.P >= kFastMinBits && n > 0) { slot[fill++] = ch.step(sm.ll, sm.ml, sm.of); n--; }
+                const bool fin = n == 0 || ch.P < kFastMinBits;
+                if (fill == (uint32_t) kSeqBatch || fin) {
+                    if (fin) { box->end_P = ch.P; box->end_states = ch.sl | (ch.sm << 10) | (ch.so << 20); active = false; }
+                    box->count[batches & (kSlots - 1)] = fill | ((seen & 0x7FFFFFu) << 8) | (fin ? kChainFinal : 0u);
+                    __threadfence_block();
+                    st_vol(&box->produced, ++batches);
+                    fill = 0;
+                }
+                worked = true;
+            }
+        }
+        if (!__any_sync(kFull, worked)) {
+            if (ld_vol(workers_done) == (uint32_t) kWorkers) return;
+            pause_ns(200);
+        }
+    }
+}
+
 
 struct Ctl {   // lane-0 results broadcast through registers
     int32_t reason;
@@ -423,7 +544,8 @@ __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n_by
 constexpr int kHufBytes = 4096 * 2, kFseBytes = (512 + 512 + 256) * 4;
 constexpr int64_t kHufSave = kMaxBlock + 256, kFseSave = kHufSave + kHufBytes;   // offsets in the warp's scratch
 
-__device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const uint8_t *in, int64_t in_addr, int block_size, uint8_t *out,
+template <bool kSvc>
+__device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameState &fs, const uint8_t *in, int64_t in_addr, int block_size, uint8_t *out,
                                            int64_t out_pos, int64_t out_cap, int32_t window_size, uint8_t *lit_scratch, bool keep_tables,
                                            Ctl &ctl, int lane)
 {
@@ -656,55 +778,82 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
         const int32_t ring_lo = oh;
         int32_t opw = oh, flushed = oh;
         const uint8_t *const bs = in + input;                            // first byte of the sequence bit stream
-        int32_t P = 0, wb = 0;                                           // lane 0: unread bits; byte position of the window
-        uint64_t w = 0;
-        bool b_stale = false;                                            // lane 0: `b` is behind P
-        if (lane == 0) P = (int32_t) (b.cur - b.start) * 8 + 64 - b.consumed;
+        Chain ch;                                                        // lane 0 (inline walk)
+        ch.bs = bs; ch.P = 0; ch.wb = 0; ch.w = 0;
+        ch.sl = (uint32_t) ll_state; ch.sm = (uint32_t) ml_state; ch.so = (uint32_t) of_state;
+        bool b_stale = false;                                            // `b` and the three states are behind the walk
+        if (lane == 0) ch.P = (int32_t) (b.cur - b.start) * 8 + 64 - b.consumed;
         const uint32_t le_mask = 0xffffffffu >> (31 - lane);             // lanes <= mine
+        uint32_t my_req = 0, my_batches = 0;                             // service kernel: my request number, batches I am done with
+        if (kSvc && wide) {
+            my_batches = box->consumed;
+            if (lane == 0) {
+                box->bs = bs; box->P = ch.P; box->n = remaining;
+                box->states = ch.sl | (ch.sm << 10) | (ch.so << 20);
+                __threadfence_block();
+                st_vol(&box->posted, box->posted + 1);
+            }
+            __syncwarp();
+            my_req = box->posted;
+        }
 
         while (remaining > 0 && !stop) {
             if (wide) {
                 int produced = 0;
-                if (lane == 0) {
-                    if (P >= kFastMinBits) {
-                        wb = (P - 57) >> 3;                               // window = bytes [wb, wb + 8): its top is 0..7 bits above P
-                        w = ld64u(bs + wb);
-                        if (wb >= 384) prefetch_l1(bs + wb - 384);        // the stream is read downwards: ask for the lines of the next batches
+                bool final_batch = false;
+                const uint2 *recs = sm.rec[0];
+                if (!kSvc) {
+                    if (lane == 0) {
+                        if (ch.P >= kFastMinBits) {
+                            ch.open();
+                            if (ch.wb >= 384) prefetch_l1(bs + ch.wb - 384);   // the stream is read downwards: ask for the lines of the next batches
+                        }
+                        while (produced < kSeqBatch && remaining > 0 && ch.P >= kFastMinBits) {
+                            sm.rec[0][produced] = ch.step(sm.ll, sm.ml, sm.of);
+                            produced++;
+                            remaining--;
+                            b_stale = true;
+                        }
                     }
-                    while (produced < kSeqBatch && remaining > 0 && P >= kFastMinBits) {
-                        const uint32_t el = sm.ll[ll_state], em = sm.ml[ml_state], eo = sm.of[of_state];
-                        sm.seq_p[produced] = (uint32_t) P;
-                        sm.seq_c[produced] = (el >> 24) | ((em >> 24) << 8) | ((eo >> 24) << 16);
-                        const int32_t P1 = P - (int32_t) (((el >> 11) & 31) + ((em >> 11) & 31) + ((eo >> 11) & 31));   // behind the extra bits
-                        int32_t sft = P1 - wb * 8;                        // the state bits are bits [sft - 26, sft) of the window
-                        if (sft < 32) { wb = (P1 - 57) >> 3; w = ld64u(bs + wb); sft = P1 - wb * 8; }
-                        uint32_t x = __funnelshift_rc((uint32_t) w, (uint32_t) (w >> 32), (uint32_t) (sft - 32));     // bits [sft - 32, sft)
-                        const uint32_t nbl = (el >> 16) & 15, nbm = (em >> 16) & 15, nbo = (eo >> 16) & 15;
-                        ll_state = (int) ((el & 0x7FF) + __funnelshift_lc(x, 0, nbl)); x <<= nbl;
-                        ml_state = (int) ((em & 0x7FF) + __funnelshift_lc(x, 0, nbm)); x <<= nbm;
-                        of_state = (int) ((eo & 0x7FF) + __funnelshift_lc(x, 0, nbo));
-                        P = P1 - (int32_t) (nbl + nbm + nbo);
-                        wb = (P - 57) >> 3;                               // next window, requested now, needed one table lookup later
-                        w = ld64u(bs + wb);
-                        produced++;
-                        remaining--;
-                        b_stale = true;
+                    produced = __shfl_sync(kFull, produced, 0);
+                    remaining = __shfl_sync(kFull, remaining, 0);
+                    final_batch = produced < kSeqBatch;
+                }
+                else {
+                    for (;;) {                                            // the next batch of MY request (older ones are dropped)
+                        while ((int32_t) (ld_vol(&box->produced) - my_batches) <= 0) pause_ns(100);
+                        __threadfence_block();
+                        const uint32_t c = box->count[my_batches & (kSlots - 1)];
+                        if (((c >> 8) & 0x7FFFFFu) == (my_req & 0x7FFFFFu)) {
+                            produced = (int) (c & 0xFF);
+                            final_batch = (c & kChainFinal) != 0;
+                            recs = sm.rec[my_batches & (kSlots - 1)];
+                            break;
+                        }
+                        __syncwarp();
+                        my_batches++;
+                        if (lane == 0) st_vol(&box->consumed, my_batches);
+                    }
+                    remaining -= produced;
+                    if (produced) b_stale = true;
+                    if (final_batch && lane == 0) {
+                        ch.P = box->end_P;
+                        const uint32_t st = box->end_states;
+                        ch.sl = st & 1023; ch.sm = (st >> 10) & 1023; ch.so = st >> 20;
                     }
                 }
 #ifdef LZS_EMU
                 if (lane == 0) emu_count_wide(produced);
 #endif
-                produced = __shfl_sync(kFull, produced, 0);
-                remaining = __shfl_sync(kFull, remaining, 0);
-                const bool leave = remaining > 0 && produced < kSeqBatch;   // close to the start of the stream: the exact loop takes over
+                const bool leave = remaining > 0 && final_batch;          // close to the start of the stream: the exact loop takes over
                 __syncwarp();
                 if (produced) {
                     // ---- every lane: the lengths and the offset code of ITS sequence
                     int32_t my_ll = 0, my_ml = 0;
                     uint32_t my_key = 0;                                  // a new offset, or 0x80000000 | repeated-offset code 0..3
                     if (lane < produced) {
-                        const int32_t ps = (int32_t) sm.seq_p[lane];
-                        const uint32_t c = sm.seq_c[lane];
+                        const int32_t ps = (int32_t) recs[lane].x;
+                        const uint32_t c = recs[lane].y;
                         const uint32_t llc = c & 0xFF, mlc = (c >> 8) & 0xFF, ofc = c >> 16;
                         int32_t a = (ps - 57) >> 3;
                         uint64_t v = ld64u(bs + a) << (64 - (ps - a * 8));   // the next unread bit is bit 63
@@ -820,15 +969,21 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
                     opw += __shfl_sync(kFull, t, 31);
                     output = abs0 + (opw - oh);
                 }
+                if (kSvc) {                                               // the slot is free again
+                    __syncwarp();
+                    my_batches++;
+                    if (lane == 0) st_vol(&box->consumed, my_batches);
+                }
                 if (leave) {
                     if (opw != flushed) ring_flush(sm.ring, out_al, flushed, opw, lane);
                     wide = false;
                     if (lane == 0 && b_stale) {                           // the state BitInputStream.load() is in at this point
-                        const int32_t cr = (P - 57) >> 3;
+                        const int32_t cr = (ch.P - 57) >> 3;
                         b.cur = b.start + cr;
-                        b.consumed = cr * 8 + 64 - P;
+                        b.consumed = cr * 8 + 64 - ch.P;
                         b.bits = ld64u(b.in + b.cur);
                         b.overflow = 0;
+                        ll_state = (int) ch.sl; ml_state = (int) ch.sm; of_state = (int) ch.so;
                     }
                 }
                 continue;
@@ -951,7 +1106,8 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, FrameState &fs, const u
 }
 
 // ZstdFrameDecompressor.decompress :135-210 for one input.  Returns output size or -1.
-__device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_cap, uint8_t *lit_scratch, Ctl &ctl, int lane)
+template <bool kSvc>
+__device__ int64_t decode_input(WarpSmem &sm, ChainBox *box, const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_cap, uint8_t *lit_scratch, Ctl &ctl, int lane)
 {
     if (out_cap == 0) return 0;
     int64_t input = 0, output = 0;
@@ -1014,7 +1170,7 @@ __device__ int64_t decode_input(WarpSmem &sm, const uint8_t *in, int64_t in_len,
                 ZCHECK(input + block_size <= in_len, input, R_NOT_ENOUGH_INPUT);
                 // does anything follow this block in the input (another block, or another frame after the checksum)?
                 const bool more_follows = !last_block || input + block_size + (has_checksum ? 4 : 0) < in_len;
-                decoded = decode_compressed_block(sm, fs, in, input, block_size, out, output, out_cap, window_size, lit_scratch, more_follows,
+                decoded = decode_compressed_block<kSvc>(sm, box, fs, in, input, block_size, out, output, out_cap, window_size, lit_scratch, more_follows,
                                                   ctl, lane);
                 if (decoded < 0) return -1;
                 input += block_size;
@@ -1059,7 +1215,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) zstd_decompress
         if ((int64_t) idx >= b.n) break;
         Ctl ctl;
         ctl.reason = 0; ctl.err_off = 0;
-        int64_t r = decode_input(sm, b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx], lit_scratch, ctl, lane);
+        int64_t r = decode_input<false>(sm, nullptr, b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx], lit_scratch, ctl, lane);
         if (lane == 0) {
             if (r >= 0) { b.out_len[idx] = r; b.status[idx] = 0; }
             else { b.out_len[idx] = ctl.err_off; b.status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
@@ -1068,6 +1224,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) zstd_decompress
     }
 }
 
+// the service kernel: kWorkers worker warps (one input each at a time, claimed from the work counter) + the chain warp
+template <int kCtasPerSm>
+__global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompress_svc_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
+{
+    extern __shared__ __align__(16) uint8_t zsmem[];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    WarpSmem *const sms = reinterpret_cast<WarpSmem *>(zsmem);
+    ChainBox *const boxes = reinterpret_cast<ChainBox *>(zsmem + (size_t) kWorkers * sizeof(WarpSmem));
+    uint32_t *const workers_done = reinterpret_cast<uint32_t *>(boxes + kWorkers);
+    if (threadIdx.x < kWorkers) {
+        ChainBox &x = boxes[threadIdx.x];
+        x.posted = 0; x.consumed = 0; x.produced = 0; x.count[0] = 0; x.count[1] = 0;
+    }
+    if (threadIdx.x == 0) *workers_done = 0;
+    __syncthreads();
+    if (warp == kWorkers) { chain_warp(boxes, sms, workers_done, lane); return; }
+    WarpSmem &sm = sms[warp];
+    uint8_t *lit_scratch = scratch + ((int64_t) blockIdx.x * kWorkers + warp) * scratch_per_warp;
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(b.work_counter, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if ((int64_t) idx >= b.n) break;
+        Ctl ctl;
+        ctl.reason = 0; ctl.err_off = 0;
+        int64_t r = decode_input<true>(sm, boxes + warp, b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx], lit_scratch, ctl, lane);
+        if (lane == 0) {
+            if (r >= 0) { b.out_len[idx] = r; b.status[idx] = 0; }
+            else { b.out_len[idx] = ctl.err_off; b.status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) atomicAdd(workers_done, 1u);
+}
 #endif  // LZS_EMU
 }  // namespace
 
@@ -1092,13 +1283,27 @@ static void launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t
     zstd_decompress_kernel<kCtasPerSm><<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
 }
 
-// ctas_per_sm: 0 = the default; 5, 6 or 7 = resident CTAs per SM the kernel is compiled for (96 / 80 / 72 registers per thread)
+constexpr int kSvcCtasPerSm = 3;
+
+static void launch_zstd_decompress_svc(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch)
+{
+    const int smem = kWorkers * (int) sizeof(WarpSmem) + kWorkers * (int) sizeof(ChainBox) + 16;
+    cudaFuncSetAttribute(zstd_decompress_svc_kernel<kSvcCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int64_t ctas = (b.n + kWorkers - 1) / kWorkers;
+    const int64_t max_ctas = (int64_t) sm_count * kSvcCtasPerSm;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    zstd_decompress_svc_kernel<kSvcCtasPerSm><<<(unsigned) ctas, (kWorkers + 1) * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
+}
+
+// ctas_per_sm: 0 = the default (the service kernel); 5, 6 or 7 = the warp-per-input kernel compiled for that many resident CTAs per
+// SM (96 / 80 / 72 registers per thread)
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, int64_t scratch_bytes)
 {
     (void) scratch_bytes;
-    const int c = ctas_per_sm ? ctas_per_sm : kZstdDecCtasPerSm;
-    if (c <= 5) launch_zstd_decompress<5>(b, sm_count, st, scratch);
-    else if (c == 6) launch_zstd_decompress<6>(b, sm_count, st, scratch);
+    if (ctas_per_sm == 0) launch_zstd_decompress_svc(b, sm_count, st, scratch);
+    else if (ctas_per_sm <= 5) launch_zstd_decompress<5>(b, sm_count, st, scratch);
+    else if (ctas_per_sm == 6) launch_zstd_decompress<6>(b, sm_count, st, scratch);
     else launch_zstd_decompress<7>(b, sm_count, st, scratch);
 }
 #endif  // LZS_EMU

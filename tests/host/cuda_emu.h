@@ -78,5 +78,6 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *) p; }
 static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh > 32 ? 32 : sh)); }
 static inline uint32_t __funnelshift_lc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) ((((((uint64_t) hi) << 32) | lo) << (sh > 32 ? 32 : sh)) >> 32); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh & 31)); }

@@ -4,7 +4,7 @@
 // exchange array carries shuffles and ballots.  tests/test_zstd_dec_emu.py compares bytes, lengths, status words and error
 // offsets with the oracle.  TEST INFRASTRUCTURE: nothing here ships; the GPU parity tests remain the gate for the kernel.
 //
-//   zstd_dec_emu <in-file> <out-file>
+//   zstd_dec_emu <in-file> <out-file> [svc]      svc: the service kernel's roles (kWorkers worker warps + the chain warp of a CTA)
 //   in-file : int32 0, int32 n, then per input { int64 in_len, int64 out_cap, int32 in_misalign, int32 out_misalign, in_len bytes }
 //   out-file: per input { int64 out_len, int32 status, out_cap + 64 bytes (the 64 guard bytes must stay 0xA5) }
 #define LZS_EMU 1
@@ -47,7 +47,6 @@ static void emu_count_exact(int n) { g_exact += n; }
 
 #include "../../aircompressor_b200/csrc/zstd_dec.cu"
 
-constexpr int kWarps = 2;
 
 int main(int argc, char **argv)
 {
@@ -79,13 +78,18 @@ int main(int argc, char **argv)
     memset(dst, 0xA5, dp + 64);
     for (int i = 0; i < n; i++) if (src_len[i]) memcpy(src + src_off[i], ins[i].data(), src_len[i]);
 
+    const bool svc = argc > 3 && !strcmp(argv[3], "svc");
     std::atomic<int> next{0};
-    EmuWarp warps[kWarps];
-    static WarpSmem smem[kWarps] __attribute__((aligned(16)));
-    std::vector<std::vector<uint8_t>> scratch(kWarps, std::vector<uint8_t>((size_t) kZstdDecScratchPerWarp + 64));
+    constexpr int kEmuWarps = kWorkers + 1;             // worker warps (+ the chain warp in svc mode)
+    EmuWarp warps[kEmuWarps];
+    static WarpSmem smem[kWorkers] __attribute__((aligned(16)));
+    static ChainBox boxes[kWorkers];
+    static uint32_t workers_done = 0;
+    memset(boxes, 0, sizeof(boxes));
+    std::vector<std::vector<uint8_t>> scratch(kWorkers, std::vector<uint8_t>((size_t) kZstdDecScratchPerWarp + 64));
     for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
     std::vector<std::thread> th;
-    for (int w = 0; w < kWarps; w++)
+    for (int w = 0; w < kWorkers; w++)
         for (int l = 0; l < 32; l++)
             th.emplace_back([&, w, l] {
                 t_warp = &warps[w]; t_lane = l;
@@ -97,14 +101,19 @@ int main(int argc, char **argv)
                     if (idx >= n) break;
                     Ctl ctl;
                     ctl.reason = 0; ctl.err_off = 0;
-                    int64_t r = decode_input(smem[w], src + src_off[idx], src_len[idx], dst + dst_off[idx], dst_cap[idx], lit_scratch, ctl, l);
+                    int64_t r = svc ? decode_input<true>(smem[w], boxes + w, src + src_off[idx], src_len[idx], dst + dst_off[idx], dst_cap[idx], lit_scratch, ctl, l)
+                                    : decode_input<false>(smem[w], nullptr, src + src_off[idx], src_len[idx], dst + dst_off[idx], dst_cap[idx], lit_scratch, ctl, l);
                     if (l == 0) {
                         if (r >= 0) { out_len[idx] = r; status[idx] = 0; }
                         else { out_len[idx] = ctl.err_off; status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
                     }
                     __syncwarp();
                 }
+                if (l == 0) __atomic_fetch_add(&workers_done, 1u, __ATOMIC_SEQ_CST);
             });
+    if (svc)
+        for (int l = 0; l < 32; l++)
+            th.emplace_back([&, l] { t_warp = &warps[kWorkers]; t_lane = l; chain_warp(boxes, smem, &workers_done, l); });
     for (auto &t : th) t.join();
 
     FILE *o = fopen(argv[2], "wb");

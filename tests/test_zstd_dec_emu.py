@@ -26,14 +26,14 @@ def emu(tmp_path_factory):
     return exe
 
 
-def run_emu(exe, tmp_path, streams, caps):
+def run_emu(exe, tmp_path, streams, caps, mode):
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(fin, "wb") as f:
         f.write(struct.pack("<ii", 0, len(streams)))
         for i, (s, cap) in enumerate(zip(streams, caps)):
             f.write(struct.pack("<qqii", len(s), cap, (i * 7) % 16, (i * 5 + 3) % 16))
             f.write(s)
-    p = subprocess.run([exe, fin, fout], check=True, timeout=1500, stderr=subprocess.PIPE, text=True)
+    p = subprocess.run([exe, fin, fout] + (["svc"] if mode == "svc" else []), check=True, timeout=1500, stderr=subprocess.PIPE, text=True)
     print(p.stderr)
     wide, exact = [int(x) for x in __import__("re").findall(r"(\d+) sequences on the wide path, (\d+) in the exact loop", p.stderr)[0]]
     assert wide > 4 * exact > 0          # both paths ran, the wide one on most sequences
@@ -86,9 +86,11 @@ def build_cases(oracle, refnative, pieces, synthetic_cases):
     return streams, caps, want, n_valid
 
 
-def test_decode_device_code_matches_oracle(emu, tmp_path, oracle, refnative, pieces, synthetic_cases):
+@pytest.mark.parametrize("mode", ["svc", "warp"])
+def test_decode_device_code_matches_oracle(emu, tmp_path, oracle, refnative, pieces, synthetic_cases, mode):
+    # svc: the service kernel's roles (worker warps + the chain warp of a CTA talking through mailboxes); warp: one warp per input
     streams, caps, want, n_valid = build_cases(oracle, refnative, pieces, synthetic_cases)
-    results = run_emu(emu, tmp_path, streams, caps)
+    results = run_emu(emu, tmp_path, streams, caps, mode)
     n_bad = n_reason_diff = 0
     for i, (s, cap) in enumerate(zip(streams, caps)):
         olen, status, data = results[i]
