@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaircompress_cuda.so")
+LIB_PATH = os.environ.get("AIRCOMPRESS_CUDA_LIB") or os.path.join(_HERE, "libaircompress_cuda.so")   # the override is for A/B builds of the same ABI
 
 OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, OP_XXH64 = range(7)
 F_DEVICE_POINTERS = 1

@@ -23,11 +23,6 @@ constexpr int kFlush = 512;                          // the ring drains in piece
 constexpr int32_t kFastMinBits = 256;                // the wide sequence path needs this many unread bits in front of a sequence
 constexpr int kHufSmemLog = 11;                      // Huffman tables up to this log live in shared memory
 constexpr int kSlots = 2;                            // record batches a worker holds (the chain lane of the service kernel runs ahead)
-#ifndef LZS_EMU
-constexpr int kWorkers = 7;                          // service kernel: worker warps per CTA (+ one chain warp)
-#else
-constexpr int kWorkers = 2;
-#endif
 
 // Shared memory of a warp, 7.4 KiB in three regions whose tenants are never live at the same time:
 //   A  the Huffman table while the literals of a block are decoded (2048 x u16: table logs up to 11, which is what the Java and
@@ -60,6 +55,12 @@ struct WarpSmem {
 };
 static_assert(sizeof(WarpSmem) == 5120 + kRing + 512 && sizeof(WarpSmem) % 16 == 0, "WarpSmem layout");
 
+#ifndef LZS_EMU
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+#else
+__device__ __forceinline__ void prefetch_l1(const void *) {}
+#endif
+
 // ---- the FSE state walk ------------------------------------------------------------------------------------------------
 // One lane, one block: table entry -> bits consumed -> next state, noting where each sequence's bits begin.  Lengths and
 // offsets are NOT assembled here (the worker's lanes do that in parallel); the next window of the stream is requested before
@@ -87,7 +88,9 @@ struct Chain {
         sm = (em & 0x7FF) + __funnelshift_lc(x, 0, nbm); x <<= nbm;
         so = (eo & 0x7FF) + __funnelshift_lc(x, 0, nbo);
         P = P1 - (int32_t) (nbl + nbm + nbo);
-        wb = (P - 57) >> 3;                               // next window, requested now, needed one table lookup later
+        const int32_t nwb = (P - 57) >> 3;                // next window, requested now, needed one table lookup later
+        if (((nwb ^ wb) & ~127) != 0 && nwb >= 384) prefetch_l1(bs + nwb - 384);   // the stream is read downwards: a new line every ~40 sequences
+        wb = nwb;
         w = ld64u(bs + wb);
         return r;
     }
@@ -126,6 +129,7 @@ __device__ __forceinline__ void pause_ns(unsigned) { sched_yield(); }
 #endif
 
 // the chain warp of a CTA: lane w serves worker w in rounds of one sequence per active lane
+template <int kWorkers>
 __device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, const uint32_t *workers_done, const int lane)
 {
     ChainBox *const box = boxes + (lane < kWorkers ? lane : 0);
@@ -168,7 +172,7 @@ __device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, const ui
             }
         }
         if (!__any_sync(kFull, worked)) {
-            if (ld_vol(workers_done) == (uint32_t) kWorkers) return;
+            if (__all_sync(kFull, ld_vol(workers_done) == (uint32_t) kWorkers)) return;   // a uniform decision: all lanes leave together
             pause_ns(200);
         }
     }
@@ -179,12 +183,6 @@ struct Ctl {   // lane-0 results broadcast through registers
     int32_t reason;
     int64_t err_off;
 };
-
-#ifndef LZS_EMU
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-#else
-__device__ __forceinline__ void prefetch_l1(const void *) {}
-#endif
 
 #define ZFAIL(reason_, off_) do { ctl.reason = (reason_); ctl.err_off = (off_); return -1; } while (0)
 #define ZCHECK(cond, off_, reason_) do { if (!(cond)) ZFAIL(reason_, off_); } while (0)
@@ -460,6 +458,32 @@ __device__ __forceinline__ void copy_literals(uint8_t *dst, const Literals &lit,
     else {
         warp_copy(dst, lit.ptr + pos, n, lane);
     }
+}
+
+// A worker that leaves an input early (malformed) must not reuse its tables while its chain lane may still be walking them:
+// it posts an empty request and waits for that request's (empty, final) batch -- the lane is idle from then on.  (Called from
+// the kernel loop, not from the decode functions: a call in there cost the hot loops registers, -20 %.)
+__device__ __noinline__ void chain_cancel(ChainBox *box, const int lane)
+{
+    uint32_t my_batches = box->consumed;
+    __syncwarp();
+    if (lane == 0) {
+        box->P = 0; box->n = 0;
+        __threadfence_block();
+        st_vol(&box->posted, box->posted + 1);
+    }
+    __syncwarp();
+    const uint32_t my_req = box->posted;
+    for (;;) {
+        while ((int32_t) (ld_vol(&box->produced) - my_batches) <= 0) pause_ns(100);
+        __threadfence_block();
+        const uint32_t c = box->count[my_batches & (kSlots - 1)];
+        __syncwarp();
+        my_batches++;
+        if (lane == 0) st_vol(&box->consumed, my_batches);
+        if (((c >> 8) & 0x7FFFFFu) == (my_req & 0x7FFFFFu)) break;
+    }
+    __syncwarp();
 }
 
 // ---- the wide sequence path: output ring -------------------------------------------------------------------------------
@@ -804,10 +828,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
                 const uint2 *recs = sm.rec[0];
                 if (!kSvc) {
                     if (lane == 0) {
-                        if (ch.P >= kFastMinBits) {
-                            ch.open();
-                            if (ch.wb >= 384) prefetch_l1(bs + ch.wb - 384);   // the stream is read downwards: ask for the lines of the next batches
-                        }
+                        if (ch.P >= kFastMinBits) ch.open();
                         while (produced < kSeqBatch && remaining > 0 && ch.P >= kFastMinBits) {
                             sm.rec[0][produced] = ch.step(sm.ll, sm.ml, sm.of);
                             produced++;
@@ -1225,7 +1246,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kCtasPerSm) zstd_decompress
 }
 
 // the service kernel: kWorkers worker warps (one input each at a time, claimed from the work counter) + the chain warp
-template <int kCtasPerSm>
+template <int kWorkers, int kCtasPerSm>
 __global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompress_svc_kernel(AccBatch b, uint8_t *scratch, int64_t scratch_per_warp)
 {
     extern __shared__ __align__(16) uint8_t zsmem[];
@@ -1240,7 +1261,7 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompre
     }
     if (threadIdx.x == 0) *workers_done = 0;
     __syncthreads();
-    if (warp == kWorkers) { chain_warp(boxes, sms, workers_done, lane); return; }
+    if (warp == kWorkers) { chain_warp<kWorkers>(boxes, sms, workers_done, lane); return; }
     WarpSmem &sm = sms[warp];
     uint8_t *lit_scratch = scratch + ((int64_t) blockIdx.x * kWorkers + warp) * scratch_per_warp;
     for (;;) {
@@ -1251,6 +1272,7 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompre
         Ctl ctl;
         ctl.reason = 0; ctl.err_off = 0;
         int64_t r = decode_input<true>(sm, boxes + warp, b.src + b.src_off[idx], b.src_len[idx], b.dst + b.dst_off[idx], b.dst_cap[idx], lit_scratch, ctl, lane);
+        if (r < 0) chain_cancel(boxes + warp, lane);   // the chain lane may still be walking this input's tables: make it stop before they are reused
         if (lane == 0) {
             if (r >= 0) { b.out_len[idx] = r; b.status[idx] = 0; }
             else { b.out_len[idx] = ctl.err_off; b.status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
@@ -1264,7 +1286,7 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompre
 
 static constexpr int64_t kZstdDecScratchPerWarp = zs::kMaxBlock + 256 + kHufBytes + kFseBytes;   // literals | parked Huffman table | parked FSE tables
 
-constexpr int kZstdDecMaxCtasPerSm = 7, kZstdDecCtasPerSm = 5;   // shared memory allows 7 CTAs x 4 warps (30 KiB each); the scratch is sized for that
+constexpr int kZstdDecMaxCtasPerSm = 7;   // the scratch is sized for 7 x 4 = 28 decoding warps per SM (the most any kernel shape keeps resident)
 
 int64_t acc_zstd_dec_grid(int sm_count) { return (int64_t) sm_count * kZstdDecMaxCtasPerSm; }
 
@@ -1283,27 +1305,30 @@ static void launch_zstd_decompress(const AccBatch &b, int sm_count, cudaStream_t
     zstd_decompress_kernel<kCtasPerSm><<<(unsigned) ctas, kWarpsPerCta * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
 }
 
-constexpr int kSvcCtasPerSm = 3;
-
+template <int kWorkers, int kCtasPerSm>
 static void launch_zstd_decompress_svc(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch)
 {
+    static_assert(kWorkers * kCtasPerSm <= kZstdDecMaxCtasPerSm * kWarpsPerCta, "scratch is sized for 28 decoding warps per SM");
     const int smem = kWorkers * (int) sizeof(WarpSmem) + kWorkers * (int) sizeof(ChainBox) + 16;
-    cudaFuncSetAttribute(zstd_decompress_svc_kernel<kSvcCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(zstd_decompress_svc_kernel<kWorkers, kCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int64_t ctas = (b.n + kWorkers - 1) / kWorkers;
-    const int64_t max_ctas = (int64_t) sm_count * kSvcCtasPerSm;
+    const int64_t max_ctas = (int64_t) sm_count * kCtasPerSm;
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    zstd_decompress_svc_kernel<kSvcCtasPerSm><<<(unsigned) ctas, (kWorkers + 1) * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
+    zstd_decompress_svc_kernel<kWorkers, kCtasPerSm><<<(unsigned) ctas, (kWorkers + 1) * 32, smem, st>>>(b, (uint8_t *) scratch, kZstdDecScratchPerWarp);
 }
 
-// ctas_per_sm: 0 = the default (the service kernel); 5, 6 or 7 = the warp-per-input kernel compiled for that many resident CTAs per
-// SM (96 / 80 / 72 registers per thread)
+// ctas_per_sm (acc_set_tuning key 0): 0 = automatic -- the service kernel, 13 workers + chain warp x 2 CTAs per SM when the batch
+// fills that shape, 7 + 1 x 3 for smaller batches (more CTAs to spread over the SMs); 173 / 232 / 371 = the service kernel as
+// 7+1 x 3, 13+1 x 2, 27+1 x 1; 5 = the warp-per-input kernel (the state walk inline on lane 0), 5 CTAs of 4 warps per SM.
+// Measured on 32,768 128 KiB Silesia blocks: 52.5 / 55.7 / 56.2 GiB/s for the three service shapes, 44-47 for the warp-per-input kernel.
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, int64_t scratch_bytes)
 {
     (void) scratch_bytes;
-    if (ctas_per_sm == 0) launch_zstd_decompress_svc(b, sm_count, st, scratch);
-    else if (ctas_per_sm <= 5) launch_zstd_decompress<5>(b, sm_count, st, scratch);
-    else if (ctas_per_sm == 6) launch_zstd_decompress<6>(b, sm_count, st, scratch);
-    else launch_zstd_decompress<7>(b, sm_count, st, scratch);
+    if (ctas_per_sm == 0) ctas_per_sm = b.n >= (int64_t) sm_count * 26 ? 232 : 173;
+    if (ctas_per_sm == 232) launch_zstd_decompress_svc<13, 2>(b, sm_count, st, scratch);
+    else if (ctas_per_sm == 371) launch_zstd_decompress_svc<27, 1>(b, sm_count, st, scratch);
+    else if (ctas_per_sm == 5) launch_zstd_decompress<5>(b, sm_count, st, scratch);
+    else launch_zstd_decompress_svc<7, 3>(b, sm_count, st, scratch);
 }
 #endif  // LZS_EMU

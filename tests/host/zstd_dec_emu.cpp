@@ -47,6 +47,8 @@ static void emu_count_exact(int n) { g_exact += n; }
 
 #include "../../aircompressor_b200/csrc/zstd_dec.cu"
 
+constexpr int kWorkers = 2;                         // worker warps of the emulated CTA
+
 
 int main(int argc, char **argv)
 {
@@ -113,7 +115,7 @@ int main(int argc, char **argv)
             });
     if (svc)
         for (int l = 0; l < 32; l++)
-            th.emplace_back([&, l] { t_warp = &warps[kWorkers]; t_lane = l; chain_warp(boxes, smem, &workers_done, l); });
+            th.emplace_back([&, l] { t_warp = &warps[kWorkers]; t_lane = l; chain_warp<kWorkers>(boxes, smem, &workers_done, l); });
     for (auto &t : th) t.join();
 
     FILE *o = fopen(argv[2], "wb");
