@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AIRCOMPRESS_CUDA_LIB") or os.path.join(_HERE, "libaircompress_cuda.so")   # the override is for A/B builds of the same ABI
 
-OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, OP_XXH64 = range(7)
+OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, OP_XXH64, OP_XXH32 = range(8)
 F_DEVICE_POINTERS = 1
 
 E_MALFORMED, E_DST_TOO_SMALL, E_ARGUMENT, E_CUDA, E_UNSUPPORTED = 1, 2, 3, 4, 5
@@ -58,6 +58,8 @@ def lib():
         "acc_xxh64": (i64, [vp, vp, i64, i64]),
         "acc_batch": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64]),
         "acc_xxh64_batch": (i32, [vp, vp, vp, vp, vp, i64, i32, i64]),
+        "acc_xxh32": (i32, [vp, vp, i64, i32]),
+        "acc_xxh32_batch": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i64]),
     }
     for codec in ("lz4", "snappy", "zstd"):
         for d in ("compress", "decompress"):

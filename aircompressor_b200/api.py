@@ -268,7 +268,7 @@ class BatchEngine:
         out_len = np.zeros(n, dtype=np.int64)
         status = np.zeros(n, dtype=np.int32)
         so, sl = np.ascontiguousarray(src_off, dtype=np.int64), np.ascontiguousarray(src_len, dtype=np.int64)
-        if op == N.OP_XXH64:
+        if op in (N.OP_XXH64, N.OP_XXH32):
             r = self._L.acc_batch(self._ctx.handle, op, src.ctypes.data, so.ctypes.data, sl.ctypes.data, None, None, None,
                                   out_len.ctypes.data, status.ctypes.data, n, 0, 0)
         else:

@@ -288,6 +288,7 @@ static int32_t enqueue(acc_ctx *c, int32_t op, AccBatch b, cudaStream_t st, uint
         }
         case ACC_OP_SNAPPY_COMPRESS: acc_launch_snappy_compress(b, c->sm_count, st); break;
         case ACC_OP_XXH64: acc_launch_xxh64(b, seed, c->sm_count, st); break;
+        case ACC_OP_XXH32: acc_launch_xxh32(b, (uint32_t) seed, c->sm_count, st); break;
         case ACC_OP_ZSTD_COMPRESS:
         case ACC_OP_ZSTD_DECOMPRESS: {
             int64_t need = zstd_scratch_bytes(op, b.n, c->sm_count);
@@ -382,7 +383,7 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
                           void *dst_base, const int64_t *dst_off, const int64_t *dst_cap, int64_t *out_len, int32_t *status,
                           int64_t n, int32_t flags, int64_t stream, uint64_t seed)
 {
-    if (!c || n < 0 || op < 0 || op > ACC_OP_XXH64) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
+    if (!c || n < 0 || op < 0 || op > ACC_OP_XXH32) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
     if (cudaSetDevice(c->device) != cudaSuccess) return -ACC_STATUS(ACC_E_CUDA, (int) cudaGetLastError());
     cudaStream_t st = stream ? (cudaStream_t) (uintptr_t) stream : c->stream;
     if (n == 0) return 0;
@@ -393,7 +394,7 @@ static int32_t batch_impl(acc_ctx *c, int32_t op, const void *src_base, const in
     }
 
     // ---- host pointers: stage, run, copy back, synchronise ----
-    const bool has_dst = op != ACC_OP_XXH64;
+    const bool has_dst = op != ACC_OP_XXH64 && op != ACC_OP_XXH32;
     int64_t src_lo = INT64_MAX, src_hi = 0, dst_lo = INT64_MAX, dst_hi = 0;
     for (int64_t i = 0; i < n; i++) {
         if (src_len[i] < 0 || src_off[i] < 0) return -ACC_STATUS(ACC_E_ARGUMENT, 0);
@@ -547,6 +548,11 @@ int32_t acc_xxh64_batch(acc_ctx *c, const void *sb, const int64_t *so, const int
     return batch_impl(c, ACC_OP_XXH64, sb, so, sl, nullptr, nullptr, nullptr, hashes, nullptr, n, flags, stream, 0);
 }
 
+int32_t acc_xxh32_batch(acc_ctx *c, const void *sb, const int64_t *so, const int64_t *sl, int64_t *hashes, int64_t n, int32_t seed, int32_t flags, int64_t stream)
+{
+    return batch_impl(c, ACC_OP_XXH32, sb, so, sl, nullptr, nullptr, nullptr, hashes, nullptr, n, flags, stream, (uint64_t) (uint32_t) seed);
+}
+
 int64_t acc_lz4_compress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_LZ4_COMPRESS, s, sl, d, dc, 0); }
 int64_t acc_lz4_decompress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_LZ4_DECOMPRESS, s, sl, d, dc, 0); }
 int64_t acc_snappy_compress(acc_ctx *c, const void *s, int64_t sl, void *d, int64_t dc) { return single_impl(c, ACC_OP_SNAPPY_COMPRESS, s, sl, d, dc, 0); }
@@ -561,6 +567,15 @@ int64_t acc_xxh64(acc_ctx *c, const void *src, int64_t len, int64_t seed)
     int32_t r = batch_impl(c, ACC_OP_XXH64, src, &zero, &len, nullptr, nullptr, nullptr, &h, nullptr, 1, 0, 0, (uint64_t) seed);
     c->last_status = r ? -r : 0;
     return h;
+}
+
+int32_t acc_xxh32(acc_ctx *c, const void *src, int64_t len, int32_t seed)
+{
+    if (!c || len < 0) return 0;
+    int64_t zero = 0, h = 0;
+    int32_t r = batch_impl(c, ACC_OP_XXH32, src, &zero, &len, nullptr, nullptr, nullptr, &h, nullptr, 1, 0, 0, (uint64_t) (uint32_t) seed);
+    c->last_status = r ? -r : 0;
+    return (int32_t) (uint32_t) h;
 }
 
 // SnappyRawDecompressor.readUncompressedLength (snappy/SnappyRawDecompressor.java:277-321): header-only, host side.

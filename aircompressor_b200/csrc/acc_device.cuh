@@ -144,5 +144,6 @@ void acc_launch_lz4_compress(const AccBatch &b, int sm_count, cudaStream_t st, u
 void acc_launch_snappy_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, unsigned int *second_counter);
 void acc_launch_snappy_compress(const AccBatch &b, int sm_count, cudaStream_t st);
 void acc_launch_xxh64(const AccBatch &b, uint64_t seed, int sm_count, cudaStream_t st);
+void acc_launch_xxh32(const AccBatch &b, uint32_t seed, int sm_count, cudaStream_t st);
 void acc_launch_zstd_decompress(const AccBatch &b, int sm_count, int ctas_per_sm, cudaStream_t st, void *scratch, int64_t scratch_bytes);
 void acc_launch_zstd_compress(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch, int64_t scratch_bytes);

@@ -126,6 +126,10 @@ int64_t acc_zstd_frame_content_size(const void *src, int64_t src_len, int64_t *e
 /* XXH64 one-shot: replaces XXH64(input, length, seed) (xxhash/XxHash64Bindings.java:32-34,81-100). */
 int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
 
+/* XXH32 one-shot: replaces XXH32(input, length, seed) (xxhash/XxHash32Bindings.java; Java: XxHash32JavaHasher.hash,
+ * xxhash/XxHash32JavaHasher.java:68-109) -- the checksum of the LZ4 frame format (lz4/Lz4FrameCompression.java:95,216,285,307). */
+int32_t acc_xxh32(acc_ctx *ctx, const void *src, int64_t len, int32_t seed);
+
 /* ---- batches of independent blocks (the GPU-shaped entry points; bound non-critical from Java).
  *      op codes select codec + direction; all share one signature so the Java record stays small. */
 #define ACC_OP_LZ4_COMPRESS      0
@@ -135,6 +139,7 @@ int64_t acc_xxh64(acc_ctx *ctx, const void *src, int64_t len, int64_t seed);
 #define ACC_OP_ZSTD_COMPRESS     4
 #define ACC_OP_ZSTD_DECOMPRESS   5
 #define ACC_OP_XXH64             6   /* out_len[i] receives the 64-bit hash (seed 0); dst_* unused (may be NULL) */
+#define ACC_OP_XXH32             7   /* out_len[i] receives the 32-bit hash, zero-extended (seed 0 through acc_batch) */
 
 /*
  * block i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes at most dst_cap[i] bytes at
@@ -169,6 +174,8 @@ int32_t acc_snappy_decompress_batch(acc_ctx *, const void *, const int64_t *, co
 int32_t acc_zstd_compress_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, void *, const int64_t *, const int64_t *, int64_t *, int32_t *, int64_t, int32_t, int64_t);
 int32_t acc_zstd_decompress_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, void *, const int64_t *, const int64_t *, int64_t *, int32_t *, int64_t, int32_t, int64_t);
 int32_t acc_xxh64_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, int64_t *, int64_t, int32_t, int64_t);
+/* (ctx, src_base, src_off, src_len, hashes, n, seed, flags, stream): XXH32 of n buffers, hashes[i] zero-extended */
+int32_t acc_xxh32_batch(acc_ctx *, const void *, const int64_t *, const int64_t *, int64_t *, int64_t, int32_t, int32_t, int64_t);
 
 /* tuning knob used by bench.py sweeps: 0 restores the default. Returns the previous value.
  * key 0: resident CTAs per SM for the warp-per-block decode kernels;

@@ -38,6 +38,7 @@ int64_t orc_batch(int32_t op, const uint8_t *src_base, const int64_t *src_off, c
             case 4: r = orc_zstd_compress(s, src_len[i], d, cap); break;
             case 5: r = orc_zstd_decompress(s, src_len[i], d, cap, 0); break;
             case 6: r = (int64_t) orc_xxh64(s, src_len[i], 0); out_len[i] = r; continue;
+            case 7: r = (int64_t) orc_xxh32(s, src_len[i], 0); out_len[i] = r; continue;
             default: r = ORC_STATUS(ORC_E_ARGUMENT, 0);
         }
         out_len[i] = r;

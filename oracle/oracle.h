@@ -71,6 +71,7 @@ int64_t orc_snappy_uncompressed_length(const uint8_t *in, int64_t in_len, int64_
 /* ---- XXH64: zstd/XxHash64.java, xxhash/XxHash64JavaHasher.java ---- */
 uint64_t orc_xxh64(const uint8_t *in, int64_t len, uint64_t seed);
 uint64_t orc_xxh64_long(uint64_t value, uint64_t seed);
+uint32_t orc_xxh32(const uint8_t *in, int64_t len, uint32_t seed);   /* xxhash/XxHash32JavaHasher.java:68-109 */
 
 /* ---- Zstandard: zstd/ZstdFrameCompressor.java, zstd/ZstdFrameDecompressor.java (+ helpers) ---- */
 int64_t orc_zstd_max_compressed_length(int64_t n);

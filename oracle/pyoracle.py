@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, OP_XXH64 = range(7)
+OP_LZ4_COMPRESS, OP_LZ4_DECOMPRESS, OP_SNAPPY_COMPRESS, OP_SNAPPY_DECOMPRESS, OP_ZSTD_COMPRESS, OP_ZSTD_DECOMPRESS, OP_XXH64, OP_XXH32 = range(8)
 
 
 def _u8(buf):
@@ -49,6 +49,8 @@ class Oracle:
         L.orc_xxh64.argtypes = [p8, i64, C.c_uint64]
         L.orc_xxh64_long.restype = C.c_uint64
         L.orc_xxh64_long.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_xxh32.restype = C.c_uint32
+        L.orc_xxh32.argtypes = [p8, i64, C.c_uint32]
         L.orc_batch.restype = i64
         L.orc_batch.argtypes = [C.c_int32, p8, pi64, pi64, p8, pi64, pi64, pi64, i64, C.c_int32]
         try:   # absent from a liboracle.so built before this entry point existed
@@ -90,6 +92,10 @@ class Oracle:
 
     def xxh64_long(self, value, seed=0):
         return self.lib.orc_xxh64_long(value & 0xFFFFFFFFFFFFFFFF, seed & 0xFFFFFFFFFFFFFFFF)
+
+    def xxh32(self, data, seed=0):
+        src, n, _k = _u8(data)
+        return self.lib.orc_xxh32(src, n, seed & 0xFFFFFFFF)
 
     def max_threads(self):
         return self.lib.orc_max_threads()
@@ -184,6 +190,8 @@ class RefNative:
         if self.xxhash:
             self.xxhash.XXH64.restype = C.c_uint64
             self.xxhash.XXH64.argtypes = [vp, sz, C.c_uint64]
+            self.xxhash.XXH32.restype = C.c_uint32
+            self.xxhash.XXH32.argtypes = [vp, sz, C.c_uint32]
 
     @staticmethod
     def _ptr(a):
@@ -263,3 +271,7 @@ class RefNative:
     def xxh64(self, data, seed=0):
         src = np.frombuffer(bytes(data), dtype=np.uint8)
         return self.xxhash.XXH64(self._ptr(src), src.size, seed & 0xFFFFFFFFFFFFFFFF)
+
+    def xxh32(self, data, seed=0):
+        src = np.frombuffer(bytes(data), dtype=np.uint8)
+        return self.xxhash.XXH32(self._ptr(src), src.size, seed & 0xFFFFFFFF)

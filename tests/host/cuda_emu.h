@@ -14,6 +14,7 @@
 #define __device__
 #define __global__
 #define __host__
+#define __noinline__ __attribute__((noinline))
 #define __forceinline__ inline __attribute__((always_inline))
 #define __constant__ const
 #define __align__(n) __attribute__((aligned(n)))

@@ -1,0 +1,108 @@
+"""CPU tests of the f1 row's checkers: the XXH32 oracle against the reference's known answers and its bundled libxxhash, the
+LZ4 frame oracle (oracle/lz4_frame_oracle.py = Lz4FrameCompression.java restated) against an independent implementation of
+the frame format (the image's liblz4 LZ4F) in both directions and against the hand-built frames of
+T/lz4/TestLz4FrameDecompressor.java:61-230, and that the C ABI exports the XXH32 entry points."""
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import lz4_frame_oracle as fo
+from lz4f_native import Lz4fNative
+
+CONTENT = b"the quick brown fox jumps over the lazy dog"
+
+
+def build_frame(oracle, flags, bd=0x70, content_size=len(CONTENT), block_checksum=None, content_checksum=None, content=CONTENT):
+    """FrameBuilder of the reference test (TestLz4FrameDecompressor.java:268-340): one stored block holding `content`."""
+    desc = bytes([fo.FLG_VERSION | flags, bd])
+    if flags & fo.FLG_CONTENT_SIZE:
+        desc += struct.pack("<q", content_size)
+    if flags & fo.FLG_DICTIONARY_ID:
+        desc += struct.pack("<I", 0xCAFEBABE)
+    f = struct.pack("<I", fo.MAGIC) + desc + bytes([(oracle.xxh32(desc) >> 8) & 0xFF])
+    f += struct.pack("<I", len(content) | fo.UNCOMPRESSED_BLOCK_FLAG) + content
+    if flags & fo.FLG_BLOCK_CHECKSUM:
+        f += struct.pack("<I", block_checksum if block_checksum is not None else oracle.xxh32(content))
+    f += struct.pack("<I", 0)
+    if flags & fo.FLG_CONTENT_CHECKSUM:
+        f += struct.pack("<I", content_checksum if content_checksum is not None else oracle.xxh32(content))
+    return f
+
+
+def skippable(content):
+    return struct.pack("<II", fo.SKIPPABLE_MAGIC, len(content)) + content
+
+
+def reference_cases(oracle):
+    """(frame, output capacity, expected bytes or expected message fragment) of T/lz4/TestLz4FrameDecompressor.java:61-230."""
+    I = fo.FLG_BLOCK_INDEPENDENCE
+    x = oracle.xxh32(CONTENT)
+    ok = build_frame(oracle, I)
+    bad_magic = bytearray(ok); bad_magic[0] ^= 0xFF
+    bad_version = bytearray(ok); bad_version[4] &= 0x3F
+    bad_hc = bytearray(ok); bad_hc[6] ^= 0xFF
+    cc = build_frame(oracle, I | fo.FLG_CONTENT_CHECKSUM)
+    sk = skippable(b"ignored metadata")
+    n = len(CONTENT)
+    return [
+        (cc, n, CONTENT),
+        (build_frame(oracle, I | fo.FLG_CONTENT_CHECKSUM, content_checksum=x ^ 1), n, "invalid content checksum"),
+        (build_frame(oracle, I | fo.FLG_BLOCK_CHECKSUM), n, CONTENT),
+        (build_frame(oracle, I | fo.FLG_BLOCK_CHECKSUM, block_checksum=x ^ 1), n, "invalid block checksum"),
+        (build_frame(oracle, I | fo.FLG_CONTENT_SIZE), n, CONTENT),
+        (build_frame(oracle, I | fo.FLG_CONTENT_SIZE, content_size=n + 1), n, "content size does not match"),
+        (build_frame(oracle, 0), n, "linked blocks are not supported"),
+        (build_frame(oracle, I | fo.FLG_DICTIONARY_ID), n, "dictionary are not supported"),
+        (build_frame(oracle, I | fo.FLG_RESERVED_MASK), n, "reserved bits"),
+        (build_frame(oracle, I, bd=0x71), n, "reserved bits"),
+        (bytes(bad_magic), n, "magic number"),
+        (bytes(bad_version), n, "Unsupported LZ4 frame version"),
+        (build_frame(oracle, I, bd=0x10), n, "block maximum size"),
+        (bytes(bad_hc), n, "invalid header checksum"),
+        (cc + cc + cc, 3 * n, CONTENT * 3),
+        (sk + ok + sk + ok + sk, 2 * n, CONTENT * 2),
+        (skippable(b"") + ok, n, CONTENT),
+        (ok + sk[:-1], n, "Truncated LZ4 skippable frame"),
+        (ok + bytes([1, 2, 3, 4, 5]), n, "magic number"),
+        (ok, n - 1, "Output buffer too small"),
+        (ok[:5], n, "Input is too short"),
+    ]
+
+
+def test_xxh32_oracle_known_answers_and_native_parity(oracle, refnative):
+    assert oracle.xxh32(b"") == 0x02CC5D05 and oracle.xxh32(b"abc") == 0x32D153FF      # T/xxhash/TestXxHash32.java:45-46
+    rng = np.random.default_rng(3)
+    data = bytes(rng.integers(0, 256, 4099, dtype=np.uint8))
+    for seed in (0, 1, 0x9E3779B1, 0xFFFFFFFF, 0x7FFFFFFF, 0x80000000):                 # SEEDS :30
+        for length in list(range(0, 67)) + [127, 128, 129, 1023, 1024, 4099]:
+            assert oracle.xxh32(data[:length], seed) == refnative.xxh32(data[:length], seed), (seed, length)
+    assert oracle.xxh32(data[5:1000]) == refnative.xxh32(data[5:1000])                  # any alignment
+
+
+def test_frame_oracle_on_the_reference_cases(oracle):
+    for i, (frame, cap, want) in enumerate(reference_cases(oracle)):
+        if isinstance(want, bytes):
+            assert fo.decompress(oracle, frame, cap) == want, i
+        else:
+            with pytest.raises(fo.FrameError, match=want):
+                fo.decompress(oracle, frame, cap)
+
+
+def test_frame_oracle_interoperates_with_liblz4(oracle, pieces):
+    nat = Lz4fNative()
+    rng = np.random.default_rng(5)
+    blobs = [b"", b"a", CONTENT * 100, pieces[0][:300000].tobytes(), bytes(rng.integers(0, 256, 70000, dtype=np.uint8)),
+             np.concatenate(pieces[3:6])[:4200000].tobytes() + CONTENT]              # more than one 4 MiB block
+    for k, blob in enumerate(blobs):
+        f = fo.compress(oracle, blob)
+        assert fo.decompress(oracle, f, len(blob)) == blob
+        assert nat.decompress(f, len(blob)) == blob                                   # liblz4 reads what the reference rules write
+        for bs, bsum, csum, csize in ((4, False, False, False), (5, True, False, True), (6, False, True, False), (7, True, True, True)):
+            g = nat.compress(blob, bs, bsum, csum, csize)
+            assert fo.decompress(oracle, g, len(blob)) == blob, (k, bs)              # and the reference rules read liblz4's frames
+
+
+def test_c_abi_exports_xxh32():
+    from aircompressor_b200 import _native as N
+    assert {"acc_xxh32", "acc_xxh32_batch"} <= set(N.exported_symbols())
