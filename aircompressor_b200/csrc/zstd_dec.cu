@@ -6,18 +6,10 @@
 // XXH64 frame checksum (:194-206).  Output and accept/reject decisions are bit-exact with the Java
 // decoder (offsets in error reports are relative to the input start).
 //
-// Mapping: one warp per input (all frames of the input, all blocks of a frame, in order).  Per warp in shared memory (7.5 KiB):
-// the Huffman decode table, then the three FSE decode tables; table-building scratch, then a 2 KiB output ring; two batches of
-// sequence records.  Lanes 0-3 decode the four Huffman streams (four symbols per refill), all 32 lanes build tables and execute
-// sequences: per batch of 32 every lane pulls the extra bits of ITS sequence out of the bit stream, repeated offsets are
-// resolved in order, two prefix sums give the positions, and the copies run as multi-sequence steps of up to 64 output bytes
-// through the ring.  The one thing that cannot be spread over lanes is the walk over the three FSE states; it only notes where
-// each sequence's bits begin.  Two kernels differ in who walks:
-//   service kernel (default)  a CTA = worker warps + one chain warp whose lane w walks for worker w (mailboxes in shared memory):
-//                             one warp instruction advances up to 13 (or 7, or 27) blocks;
-//   warp-per-input kernel     lane 0 of the warp itself.
-// Near the start of a bit stream, for RLE literals and for 12-bit Huffman tables the exact restatement of the Java loops runs.
-// The kernel is bound by warp instructions in flight on the ALU pipe, not by memory: DESIGN.md has the measurements.
+// Mapping: one warp per input (all frames of the input, all blocks of a frame, in order).  Per warp in
+// shared memory: the Huffman decode table (4096 x u16), three FSE decode tables (512/512/256 x u32) and
+// a 32-entry sequence batch.  Lane 0 parses headers and walks the FSE state chain, lanes 0-3 decode the
+// four Huffman streams, all 32 lanes build tables and execute literal / match copies.
 #include "zstd_common.cuh"
 #include "xxh64_device.cuh"
 
@@ -73,63 +65,15 @@ __device__ __forceinline__ void prefetch_l1(const void *) {}
 // One lane, one block: table entry -> bits consumed -> next state, noting where each sequence's bits begin.  Lengths and
 // offsets are NOT assembled here (the worker's lanes do that in parallel); the next window of the stream is requested before
 // it is needed.  Valid while at least kFastMinBits unread bits lie in front of a sequence.
-// kStaged: the stream reaches the lane through a private ring of sixteen 16-byte chunks in shared memory, filled by cp.async
-// twelve chunks (~40 sequences) ahead of the walk: the chain warp of the service kernel runs its lanes in lockstep, so ONE lane
-// waiting for L2 or DRAM would stop all the blocks of the CTA -- with the ring no lane ever waits for global memory after the
-// first window.  !kStaged (lane 0 of a warp-per-input kernel): 8-byte windows straight from global memory, requested one
-// table lookup before they are needed, lines prefetched ahead.
-#ifndef LZS_EMU
-__device__ __forceinline__ void stage_chunk(uint8_t *dst, const uint8_t *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" :: "r"((uint32_t) __cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-template <int kPending> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(kPending) : "memory"); }
-#else
-__device__ __forceinline__ void stage_chunk(uint8_t *dst, const uint8_t *src) { memcpy(dst, src, 16); }
-template <int kPending> __device__ __forceinline__ void stage_wait() {}
-#endif
-constexpr int kStageChunks = 16, kStageAhead = 12, kStageBytes = kStageChunks * 16;
-
-template <bool kStaged>
 struct Chain {
     const uint8_t *bs;        // first byte of the sequence bit stream
     int32_t P, wb;            // unread bits; byte position of the window
     uint64_t w;               // bytes [wb, wb + 8) of the stream
     uint32_t sl, sm, so;      // the three states
-    // kStaged only: chunk c holds bytes [16 c, 16 c + 16) counted from `abase` = bs rounded down to 16
-    uint8_t *stage;           // the ring (256 bytes of shared memory, 16-byte aligned): chunk c lives at stage + (c % 16) * 16
-    const uint8_t *abase;
-    int32_t boff;             // bs - abase
-    int32_t req_lo, have_lo;  // lowest chunk requested / known to have landed
-
-    __device__ __forceinline__ void fetch()   // w = bytes [wb, wb + 8)
-    {
-        if (!kStaged) { w = ld64u(bs + wb); return; }
-        const int32_t a = boff + wb, c = a >> 4;
-        const int32_t want = c - kStageAhead > 0 ? c - kStageAhead : 0;
-        while (req_lo > want) { req_lo--; stage_chunk(stage + ((req_lo & (kStageChunks - 1)) << 4), abase + ((int64_t) req_lo << 4)); }
-        if (c < have_lo) {   // first touch of chunk c: everything but the kStageAhead requests behind it must have landed
-            if (req_lo == c - kStageAhead) stage_wait<kStageAhead>(); else stage_wait<0>();
-            have_lo = c;
-        }
-        const int32_t a0 = a & ~3;
-        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(stage + (a0 & (kStageBytes - 1)));
-        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(stage + ((a0 + 4) & (kStageBytes - 1)));
-        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(stage + ((a0 + 8) & (kStageBytes - 1)));
-        const uint32_t sh = (uint32_t) (a & 3) * 8;
-        w = (uint64_t) __funnelshift_r(w0, w1, sh) | ((uint64_t) __funnelshift_r(w1, w2, sh) << 32);
-    }
     __device__ __forceinline__ void open()
     {
         wb = (P - 57) >> 3;   // the window's top is 0..7 bits above P
-        if (kStaged) {
-            abase = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(bs) & ~(uintptr_t) 15);
-            boff = (int32_t) (bs - abase);
-            const int32_t c = (boff + wb) >> 4;
-            req_lo = c + 2;   // chunks c and c + 1 hold the first window
-            have_lo = c + 2;
-        }
-        fetch();
+        w = ld64u(bs + wb);
     }
     __device__ __forceinline__ uint2 step(const uint32_t *ll, const uint32_t *ml, const uint32_t *of)
     {
@@ -137,7 +81,7 @@ struct Chain {
         const uint2 r = make_uint2((uint32_t) P, (el >> 24) | ((em >> 24) << 8) | ((eo >> 24) << 16));
         const int32_t P1 = P - (int32_t) (((el >> 11) & 31) + ((em >> 11) & 31) + ((eo >> 11) & 31));   // behind the extra bits
         int32_t sft = P1 - wb * 8;                        // the state bits are bits [sft - 26, sft) of the window
-        if (sft < 32) { wb = (P1 - 57) >> 3; fetch(); sft = P1 - wb * 8; }
+        if (sft < 32) { wb = (P1 - 57) >> 3; w = ld64u(bs + wb); sft = P1 - wb * 8; }
         uint32_t x = __funnelshift_rc((uint32_t) w, (uint32_t) (w >> 32), (uint32_t) (sft - 32));     // bits [sft - 32, sft)
         const uint32_t nbl = (el >> 16) & 15, nbm = (em >> 16) & 15, nbo = (eo >> 16) & 15;
         sl = (el & 0x7FF) + __funnelshift_lc(x, 0, nbl); x <<= nbl;
@@ -145,9 +89,9 @@ struct Chain {
         so = (eo & 0x7FF) + __funnelshift_lc(x, 0, nbo);
         P = P1 - (int32_t) (nbl + nbm + nbo);
         const int32_t nwb = (P - 57) >> 3;                // next window, requested now, needed one table lookup later
-        if (!kStaged && ((nwb ^ wb) & ~127) != 0 && nwb >= 384) prefetch_l1(bs + nwb - 384);   // read downwards: a new line every ~40 sequences
+        if (((nwb ^ wb) & ~127) != 0 && nwb >= 384) prefetch_l1(bs + nwb - 384);   // the stream is read downwards: a new line every ~40 sequences
         wb = nwb;
-        fetch();
+        w = ld64u(bs + wb);
         return r;
     }
 };
@@ -172,7 +116,6 @@ struct ChainBox {
     int32_t end_P;            // with the final batch: where the walk stopped
     uint32_t end_states;
 };
-static_assert(sizeof(ChainBox) % 16 == 0, "the staging rings behind the mailboxes are 16-byte aligned");
 constexpr uint32_t kChainFinal = 0x80000000u;
 
 #ifndef LZS_EMU
@@ -187,7 +130,7 @@ __device__ __forceinline__ void pause_ns(unsigned) { sched_yield(); }
 
 // the chain warp of a CTA: lane w serves worker w in rounds of one sequence per active lane
 template <int kWorkers>
-__device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, uint8_t *stages, const uint32_t *workers_done, const int lane)
+__device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, const uint32_t *workers_done, const int lane)
 {
     ChainBox *const box = boxes + (lane < kWorkers ? lane : 0);
     const WarpSmem &sm = sms[lane < kWorkers ? lane : 0];
@@ -196,9 +139,8 @@ __device__ void chain_warp(ChainBox *boxes, const struct WarpSmem *sms, uint8_t 
     bool active = false;
     uint32_t seen = 0, batches = 0, fill = 0;
     int32_t n = 0;
-    Chain<true> ch;
+    Chain ch;
     ch.bs = nullptr; ch.P = 0; ch.wb = 0; ch.w = 0; ch.sl = ch.sm = ch.so = 0;
-    ch.stage = stages + (lane < kWorkers ? lane : 0) * kStageBytes; ch.abase = nullptr; ch.boff = 0; ch.req_lo = ch.have_lo = 0;
     for (;;) {
         bool worked = false;
         if (serving) {
@@ -860,7 +802,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
         const int32_t ring_lo = oh;
         int32_t opw = oh, flushed = oh;
         const uint8_t *const bs = in + input;                            // first byte of the sequence bit stream
-        Chain<false> ch;                                                 // lane 0 (inline walk)
+        Chain ch;                                                        // lane 0 (inline walk)
         ch.bs = bs; ch.P = 0; ch.wb = 0; ch.w = 0;
         ch.sl = (uint32_t) ll_state; ch.sm = (uint32_t) ml_state; ch.so = (uint32_t) of_state;
         bool b_stale = false;                                            // `b` and the three states are behind the walk
@@ -900,7 +842,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
                 }
                 else {
                     for (;;) {                                            // the next batch of MY request (older ones are dropped)
-                        while ((int32_t) (ld_vol(&box->produced) - my_batches) <= 0) pause_ns(400);
+                        while ((int32_t) (ld_vol(&box->produced) - my_batches) <= 0) pause_ns(100);
                         __threadfence_block();
                         const uint32_t c = box->count[my_batches & (kSlots - 1)];
                         if (((c >> 8) & 0x7FFFFFu) == (my_req & 0x7FFFFFu)) {
@@ -1312,15 +1254,14 @@ __global__ void __launch_bounds__((kWorkers + 1) * 32, kCtasPerSm) zstd_decompre
     const int warp = threadIdx.x >> 5;
     WarpSmem *const sms = reinterpret_cast<WarpSmem *>(zsmem);
     ChainBox *const boxes = reinterpret_cast<ChainBox *>(zsmem + (size_t) kWorkers * sizeof(WarpSmem));
-    uint8_t *const stages = reinterpret_cast<uint8_t *>(boxes + kWorkers);   // sizeof(ChainBox) is a multiple of 16
-    uint32_t *const workers_done = reinterpret_cast<uint32_t *>(stages + kWorkers * kStageBytes);
+    uint32_t *const workers_done = reinterpret_cast<uint32_t *>(boxes + kWorkers);
     if (threadIdx.x < kWorkers) {
         ChainBox &x = boxes[threadIdx.x];
         x.posted = 0; x.consumed = 0; x.produced = 0; x.count[0] = 0; x.count[1] = 0;
     }
     if (threadIdx.x == 0) *workers_done = 0;
     __syncthreads();
-    if (warp == kWorkers) { chain_warp<kWorkers>(boxes, sms, stages, workers_done, lane); return; }
+    if (warp == kWorkers) { chain_warp<kWorkers>(boxes, sms, workers_done, lane); return; }
     WarpSmem &sm = sms[warp];
     uint8_t *lit_scratch = scratch + ((int64_t) blockIdx.x * kWorkers + warp) * scratch_per_warp;
     for (;;) {
@@ -1368,7 +1309,7 @@ template <int kWorkers, int kCtasPerSm>
 static void launch_zstd_decompress_svc(const AccBatch &b, int sm_count, cudaStream_t st, void *scratch)
 {
     static_assert(kWorkers * kCtasPerSm <= kZstdDecMaxCtasPerSm * kWarpsPerCta, "scratch is sized for 28 decoding warps per SM");
-    const int smem = kWorkers * ((int) sizeof(WarpSmem) + (int) sizeof(ChainBox) + kStageBytes) + 16;
+    const int smem = kWorkers * (int) sizeof(WarpSmem) + kWorkers * (int) sizeof(ChainBox) + 16;
     cudaFuncSetAttribute(zstd_decompress_svc_kernel<kWorkers, kCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int64_t ctas = (b.n + kWorkers - 1) / kWorkers;
     const int64_t max_ctas = (int64_t) sm_count * kCtasPerSm;

@@ -241,11 +241,10 @@ class Lz4FrameCudaDecompressor:
                             error = fail(p + b.length, "Truncated LZ4 frame: missing block checksum"); break
                     p += b.length + (4 if block_checksum else 0)
                 if error is not None:
-                    fr.error = error
                     break
                 if flg & FLG_CONTENT_CHECKSUM:
                     if p + 4 > n_in:
-                        fr.error = error = fail(p, "Truncated LZ4 frame: missing content checksum"); break
+                        error = fail(p, "Truncated LZ4 frame: missing content checksum"); break
                     fr.content_checksum_pos = p
                     p += 4
                 fr.end_pos = p
@@ -260,6 +259,9 @@ class Lz4FrameCudaDecompressor:
                 pos = end
             else:
                 error = fail(pos, "Invalid LZ4 frame magic number"); break
+        if error is not None and frames and frames[-1].end_pos < 0:
+            frames[-1].error = error          # found inside the last frame: reported after the blocks it had collected until then
+            error = None
         return frames, blocks, error
 
     def decompress(self, input, inputOffset, inputLength, output, outputOffset, maxOutputLength):

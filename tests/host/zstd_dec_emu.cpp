@@ -86,7 +86,6 @@ int main(int argc, char **argv)
     EmuWarp warps[kEmuWarps];
     static WarpSmem smem[kWorkers] __attribute__((aligned(16)));
     static ChainBox boxes[kWorkers];
-    static uint8_t stages[kWorkers * kStageBytes] __attribute__((aligned(16)));   // the chain lanes' staging rings
     static uint32_t workers_done = 0;
     memset(boxes, 0, sizeof(boxes));
     std::vector<std::vector<uint8_t>> scratch(kWorkers, std::vector<uint8_t>((size_t) kZstdDecScratchPerWarp + 64));
@@ -106,7 +105,6 @@ int main(int argc, char **argv)
                     ctl.reason = 0; ctl.err_off = 0;
                     int64_t r = svc ? decode_input<true>(smem[w], boxes + w, src + src_off[idx], src_len[idx], dst + dst_off[idx], dst_cap[idx], lit_scratch, ctl, l)
                                     : decode_input<false>(smem[w], nullptr, src + src_off[idx], src_len[idx], dst + dst_off[idx], dst_cap[idx], lit_scratch, ctl, l);
-                    if (svc && r < 0) chain_cancel(boxes + w, l);
                     if (l == 0) {
                         if (r >= 0) { out_len[idx] = r; status[idx] = 0; }
                         else { out_len[idx] = ctl.err_off; status[idx] = ACC_STATUS(ACC_E_MALFORMED, ctl.reason); }
@@ -117,7 +115,7 @@ int main(int argc, char **argv)
             });
     if (svc)
         for (int l = 0; l < 32; l++)
-            th.emplace_back([&, l] { t_warp = &warps[kWorkers]; t_lane = l; chain_warp<kWorkers>(boxes, smem, stages, &workers_done, l); });
+            th.emplace_back([&, l] { t_warp = &warps[kWorkers]; t_lane = l; chain_warp<kWorkers>(boxes, smem, &workers_done, l); });
     for (auto &t : th) t.join();
 
     FILE *o = fopen(argv[2], "wb");

@@ -106,3 +106,86 @@ def test_frame_oracle_interoperates_with_liblz4(oracle, pieces):
 def test_c_abi_exports_xxh32():
     from aircompressor_b200 import _native as N
     assert {"acc_xxh32", "acc_xxh32_batch"} <= set(N.exported_symbols())
+
+
+class _MockEngine:
+    """Stands in for BatchEngine in the HOST-LOGIC test below: same run_host contract, blocks decoded / compressed by the oracle."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def run_host(self, op, src, so, sl, dst, do, dc):
+        import aircompressor_b200 as acb
+        n = len(so)
+        out_len, status = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            blk = bytes(src[int(so[i]):int(so[i]) + int(sl[i])])
+            if op == acb.OP_LZ4_DECOMPRESS:
+                r, off, data = self.o.decompress_raw("lz4", blk, int(dc[i]))
+                if r < 0:
+                    status[i], out_len[i] = -r, off
+                else:
+                    dst[int(do[i]):int(do[i]) + r] = data[:r]
+                    out_len[i] = r
+            else:
+                c = self.o.compress("lz4", blk)
+                dst[int(do[i]):int(do[i]) + len(c)] = np.frombuffer(c, dtype=np.uint8)
+                out_len[i] = len(c)
+        return out_len, status
+
+
+class _MockXxh32:
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def hash(self, arr, offset, length, seed=0):
+        return self.o.xxh32(bytes(arr[offset:offset + length]), seed)
+
+    def hash_many(self, arr, offsets, lengths, seed=0):
+        return np.array([self.o.xxh32(bytes(arr[o:o + n]), seed) for o, n in zip(offsets, lengths)], dtype=np.int64)
+
+
+def test_frame_host_logic_reports_in_the_order_of_the_java_loop(oracle, pieces):
+    """The frame decoder's host side (header walk first, blocks as a batch, errors in the order the sequential Java loop meets
+    them) with the GPU calls replaced by the oracle: every outcome -- bytes, or message and offset -- equals the frame oracle's.
+    (The product has no such fallback; tests/test_gpu_lz4_frame.py runs the same cases through the CUDA library.)"""
+    import aircompressor_b200 as acb
+    from aircompressor_b200.lz4_frame import Lz4FrameCudaDecompressor
+    dec = object.__new__(Lz4FrameCudaDecompressor)
+    dec._engine, dec._x = _MockEngine(oracle), _MockXxh32(oracle)
+    nat = Lz4fNative()
+    rng = np.random.default_rng(17)
+    blob = pieces[1][:200000].tobytes()
+    cases = [(f, cap) for f, cap, _w in reference_cases(oracle)]
+    base = [fo.compress(oracle, blob), nat.compress(blob, 4, True, True, True), nat.compress(blob, 5, True, False, False)]
+    cases += [(f, len(blob)) for f in base] + [(base[0] + base[1], 2 * len(blob))]
+    for f in base:
+        for _ in range(40):
+            m = bytearray(f)
+            kind = rng.integers(0, 3)
+            if kind == 0:
+                m = m[:rng.integers(1, len(m))]
+            elif kind == 1:
+                m[rng.integers(0, len(m))] ^= 1 << rng.integers(0, 8)
+            else:
+                m[rng.integers(0, min(len(m), 24))] = rng.integers(0, 256)
+            cases.append((bytes(m), len(blob) if rng.integers(0, 4) else int(rng.integers(0, len(blob)))))
+    n_bad = 0
+    for i, (frame, cap) in enumerate(cases):
+        out = np.full(cap + 8, 0xA5, dtype=np.uint8)
+        try:
+            want = fo.decompress(oracle, frame, cap)
+        except fo.FrameError as e:
+            n_bad += 1
+            with pytest.raises(acb.MalformedInputException) as got:
+                dec.decompress(frame, 0, len(frame), out, 0, cap)
+            assert (got.value.reason, got.value.offset) == (e.reason, e.offset), i
+            continue
+        except fo.BlockError:
+            n_bad += 1
+            with pytest.raises(acb.MalformedInputException):
+                dec.decompress(frame, 0, len(frame), out, 0, cap)
+            continue
+        n = dec.decompress(frame, 0, len(frame), out, 0, cap)
+        assert n == len(want) and out[:n].tobytes() == want and (out[cap:] == 0xA5).all(), i
+    assert n_bad > 40
