@@ -36,7 +36,7 @@ constexpr int kSlots = 2;                            // record batches a worker 
 struct WarpSmem {
     union {
         uint16_t huf[2048];                       // symbol | nbits << 8
-        struct { uint32_t ll[512], ml[512], of[256]; };   // new_state (11) | extra bits of the code (5) << 11 | nbits (8) << 16 | symbol (8) << 24
+        struct { uint32_t ll[512], ml[512], of[256]; };   // sequence tables after the fix-up pass: new_state (10) | 2 zero bits | extra bits of the code << 12 (7 wide) | nbits << 19 (5 wide) | symbol << 24: three entries ADD without a carry between fields
     };
     union {
         uint8_t ring[kRing];                      // the newest output bytes of the block being executed (16-byte aligned: offset 5120)
@@ -78,16 +78,17 @@ struct Chain {
     __device__ __forceinline__ uint2 step(const uint32_t *ll, const uint32_t *ml, const uint32_t *of)
     {
         const uint32_t el = ll[sl], em = ml[sm], eo = of[so];
-        const uint2 r = make_uint2((uint32_t) P, (el >> 24) | ((em >> 24) << 8) | ((eo >> 24) << 16));
-        const int32_t P1 = P - (int32_t) (((el >> 11) & 31) + ((em >> 11) & 31) + ((eo >> 11) & 31));   // behind the extra bits
+        const uint32_t sum = el + em + eo;                // extra-bit total in bits 12-18, state-bit total in bits 19-23 (the fields cannot carry)
+        const uint2 r = make_uint2((uint32_t) P, __byte_perm(__byte_perm(el, em, 0x4473), eo, 0x4710));   // the three codes (bytes 0-2)
+        const int32_t P1 = P - (int32_t) ((sum >> 12) & 0x7F);   // behind the extra bits
         int32_t sft = P1 - wb * 8;                        // the state bits are bits [sft - 26, sft) of the window
         if (sft < 32) { wb = (P1 - 57) >> 3; w = ld64u(bs + wb); sft = P1 - wb * 8; }
         uint32_t x = __funnelshift_rc((uint32_t) w, (uint32_t) (w >> 32), (uint32_t) (sft - 32));     // bits [sft - 32, sft)
-        const uint32_t nbl = (el >> 16) & 15, nbm = (em >> 16) & 15, nbo = (eo >> 16) & 15;
-        sl = (el & 0x7FF) + __funnelshift_lc(x, 0, nbl); x <<= nbl;
-        sm = (em & 0x7FF) + __funnelshift_lc(x, 0, nbm); x <<= nbm;
-        so = (eo & 0x7FF) + __funnelshift_lc(x, 0, nbo);
-        P = P1 - (int32_t) (nbl + nbm + nbo);
+        const uint32_t nbl = (el >> 19) & 31, nbm = (em >> 19) & 31, nbo = (eo >> 19) & 31;
+        sl = (el & 0x3FF) + __funnelshift_lc(x, 0, nbl); x <<= nbl;
+        sm = (em & 0x3FF) + __funnelshift_lc(x, 0, nbm); x <<= nbm;
+        so = (eo & 0x3FF) + __funnelshift_lc(x, 0, nbo);
+        P = P1 - (int32_t) ((sum >> 19) & 0x1F);
         const int32_t nwb = (P - 57) >> 3;                // next window, requested now, needed one table lookup later
         if (((nwb ^ wb) & ~127) != 0 && nwb >= 384) prefetch_l1(bs + nwb - 384);   // the stream is read downwards: a new line every ~40 sequences
         wb = nwb;
@@ -748,15 +749,16 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
         fs.of_log = __shfl_sync(kFull, lg[1], 0);
         fs.ml_log = __shfl_sync(kFull, lg[2], 0);
         __syncwarp();
-        // the number of extra bits of every code goes into its table entries (bits 11-15): the state walk of the wide path
-        // then needs no second lookup.  Tables brought back from the parking area already carry them.
+        // re-pack the entries (layout at WarpSmem): the number of extra bits of every code goes in, so the state walk needs no
+        // second lookup, and the fields are placed so that the three entries of a sequence add without carries.  Tables brought back from the parking area already carry them.
         for (int k = 0; k < 3; k++) {
             if (((type >> (6 - 2 * k)) & 3) == 3) continue;
             uint32_t *tab = k == 0 ? sm.ll : k == 1 ? sm.of : sm.ml;
             const int size = 1 << (k == 0 ? fs.ll_log : k == 1 ? fs.of_log : fs.ml_log);
             for (int i = lane; i < size; i += 32) {
                 const uint32_t e = tab[i], sym = e >> 24;
-                tab[i] = e | ((k == 0 ? (uint32_t) kLLBits[sym] : k == 1 ? sym : (uint32_t) kMLBits[sym]) << 11);
+                const uint32_t ext = k == 0 ? (uint32_t) kLLBits[sym] : k == 1 ? sym : (uint32_t) kMLBits[sym];
+                tab[i] = (e & 0x3FF) | (ext << 12) | (((e >> 16) & 0x1F) << 19) | (e & 0xFF000000u);
             }
         }
         __syncwarp();
@@ -875,7 +877,7 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
                     if (lane < produced) {
                         const int32_t ps = (int32_t) recs[lane].x;
                         const uint32_t c = recs[lane].y;
-                        const uint32_t llc = c & 0xFF, mlc = (c >> 8) & 0xFF, ofc = c >> 16;
+                        const uint32_t llc = c & 0xFF, mlc = (c >> 8) & 0xFF, ofc = (c >> 16) & 0xFF;
                         int32_t a = (ps - 57) >> 3;
                         uint64_t v = ld64u(bs + a) << (64 - (ps - a * 8));   // the next unread bit is bit 63
                         const uint32_t ofx = (uint32_t) ((v >> 1) >> (63 - ofc));
@@ -1048,9 +1050,9 @@ __device__ int64_t decode_compressed_block(WarpSmem &sm, ChainBox *box, FrameSta
                     if (ll_code > 15) { lit_length += (int32_t) peek_bits(b.consumed, b.bits, ll_bits); b.consumed += ll_bits; }
                     if (ll_bits + ml_bits + of_bits > 64 - 7 - (9 + 9 + 8)) br_load(b);
                     int nb;
-                    nb = (el >> 16) & 0xFF; ll_state = (int) ((el & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
-                    nb = (em >> 16) & 0xFF; ml_state = (int) ((em & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
-                    nb = (eof >> 16) & 0xFF; of_state = (int) ((eof & 0x7FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (el >> 19) & 0x1F; ll_state = (int) ((el & 0x3FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (em >> 19) & 0x1F; ml_state = (int) ((em & 0x3FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
+                    nb = (eof >> 19) & 0x1F; of_state = (int) ((eof & 0x3FF) + (uint32_t) peek_bits(b.consumed, b.bits, nb)); b.consumed += nb;
                     sm.seq_ll[produced] = lit_length;
                     sm.seq_ml[produced] = match_length;
                     sm.seq_of[produced] = offset;

@@ -80,5 +80,12 @@ template <typename T> static inline T __ldcg(const T *p) { return *(const volati
 static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh > 32 ? 32 : sh)); }
 static inline uint32_t __funnelshift_lc(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) ((((((uint64_t) hi) << 32) | lo) << (sh > 32 ? 32 : sh)) >> 32); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t v = ((uint64_t) y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t) ((v >> (((s >> (4 * i)) & 7) * 8)) & 0xFF) << (8 * i);
+    return r;
+}
 static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t) (((((uint64_t) hi) << 32) | lo) >> (sh & 31)); }
