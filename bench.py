@@ -27,7 +27,7 @@ import benchdata  # noqa: E402
 GiB = float(1 << 30)
 CODEC_OPS = {
     ("lz4", "decompress"): 1, ("lz4", "compress"): 0, ("snappy", "decompress"): 3, ("snappy", "compress"): 2,
-    ("zstd", "decompress"): 5, ("zstd", "compress"): 4, ("xxh64", "hash"): 6,
+    ("zstd", "decompress"): 5, ("zstd", "compress"): 4, ("xxh64", "hash"): 6, ("xxh32", "hash"): 7,
 }
 
 
@@ -159,7 +159,7 @@ def _build_workload(codec, block_kib, n_blocks, orc, threads):
     label, pieces = benchdata.load_pieces()
     blocks = benchdata.cut_blocks(pieces, block_kib * 1024)
     raw, raw_off, raw_len = benchdata.pack(blocks)
-    if codec == "xxh64":
+    if codec in ("xxh64", "xxh32"):
         return {"label": label, "distinct": len(blocks), "raw": raw, "raw_off": raw_off, "raw_len": raw_len,
                 "comp": raw, "comp_off": raw_off, "comp_len": raw_len, "n": n_blocks}
     bound = orc.max_compressed_length(codec, int(raw_len.max()))
@@ -318,7 +318,8 @@ class DeviceRun:
             got = self.out_len_d[:d].cpu().numpy()
             for i in range(0, d, max(1, d // 16)):
                 blk = wl["raw"][wl["raw_off"][i]:wl["raw_off"][i] + wl["raw_len"][i]]
-                assert int(got[i]) & 0xFFFFFFFFFFFFFFFF == self.orc.xxh64(blk.tobytes(), 0), "xxh64 mismatch"
+                want = self.orc.xxh64(blk.tobytes(), 0) if self.op == 6 else self.orc.xxh32(blk.tobytes(), 0)
+                assert int(got[i]) & 0xFFFFFFFFFFFFFFFF == want, "hash mismatch"
         elif self.opname == "decompress":
             assert bool((self.out_len_d == self.raw_len_d).all())
             end = int(self.raw_off_h[-1] + self.raw_len_h[-1])
@@ -352,7 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd", "xxh64"])
+    ap.add_argument("--codec", default="lz4", choices=["lz4", "snappy", "zstd", "xxh64", "xxh32"])
     ap.add_argument("--op", default="decompress", choices=["compress", "decompress"])
     ap.add_argument("--block-kib", type=int, default=0, help="default 64 (lz4/snappy) or 128 (zstd)")
     ap.add_argument("--blocks", type=int, default=0, help="default: 4 GiB of uncompressed data per GPU")
@@ -367,7 +368,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--profile", action="store_true", help="profiling run (under ncu): no e2e, no cpu baseline, warm-up as given")
     args = ap.parse_args()
-    if args.codec == "xxh64":
+    if args.codec in ("xxh64", "xxh32"):
         args.op = "hash"
     if args.block_kib == 0:
         args.block_kib = 128 if args.codec == "zstd" else 64

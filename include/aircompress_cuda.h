@@ -149,8 +149,8 @@ int32_t acc_xxh32(acc_ctx *ctx, const void *src, int64_t len, int32_t seed);
  * every launch takes one or two of the context's 256 work-stealing counters, which are reused round-robin).
  * Batches of ONE context are ordered: a batch enqueued on a different stream than the previous one first waits for
  * it (the context's scratch and counters are shared), so use one context per concurrent stream of work.
- * Device buffers: kernels read whole aligned words (4 bytes; 8 in the XXH64 kernel, 32 in the parse kernel of the record
- * path), i.e. a few bytes in front of / behind a block's [src_off, src_off + src_len) range -- never beyond the
+ * Device buffers: kernels read whole aligned words (4 bytes; 8 in the XXH64 kernel, 16 in the XXH32 kernel, 32 in the parse
+ * kernel of the record path), i.e. a few bytes in front of / behind a block's [src_off, src_off + src_len) range -- never beyond the
  * 32-byte-aligned extent of src_base's allocation (cudaMalloc sizes are multiples of 256 bytes), so pad a sub-allocated
  * source buffer to a multiple of 32 bytes.
  * Without it the library copies host->device,
