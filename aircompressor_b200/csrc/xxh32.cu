@@ -15,21 +15,15 @@ __device__ __forceinline__ uint32_t rotl32(uint32_t v, int r) { return __funnels
 __device__ __forceinline__ uint32_t mix32(uint32_t cur, uint32_t v) { return rotl32(cur + v * Q2, 13) * Q1; }
 
 // The batch kernel stages the input in shared memory: a warp serves eight buffers at a time, and for each of them all 32
-// lanes fetch one 512-byte chunk with 16-byte cp.async copies (one fully used wavefront per 512 bytes instead of one per 16; the
-// next chunk lands while this one is hashed), then the
+// lanes fetch one 512-byte chunk with 16-byte loads (one fully used wavefront per 512 bytes instead of one per 16), then the
 // buffer's four lanes read their words back from shared memory (rows 544 bytes apart: the eight groups hit disjoint banks).
 // Any alignment: the chunk starts at the 16-byte aligned address below the buffer, a lane assembles its word from two shared
 // words when the buffer is not 4-byte aligned.  The accumulator chains and the tail are those of xxh32_group4.
-constexpr int kChunk = 512, kRow = kChunk + 32, kWarps = 4;
-
-__device__ __forceinline__ void copy16_async(void *dst_smem, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
+constexpr int kChunk = 512, kRow = kChunk + 32, kWarps = 8;
 
 __global__ void __launch_bounds__(kWarps * 32) xxh32_kernel(AccBatch b, uint32_t seed)
 {
-    __shared__ __align__(16) uint8_t stage[kWarps][2][8][kRow];     // two chunks per buffer: chunk c + 1 lands (cp.async) while chunk c is hashed
+    __shared__ __align__(16) uint8_t stage[kWarps][8][kRow];
     const int lane = lane_id();
     const int sub = lane & 3;           // accumulator index
     const int grp = lane >> 2;          // buffer slot inside the warp
@@ -50,28 +44,22 @@ __global__ void __launch_bounds__(kWarps * 32) xxh32_kernel(AccBatch b, uint32_t
         const int64_t my_chunks = (stripes + 31) >> 5;                    // 32 stripes per chunk
         int64_t max_chunks = my_chunks;
         for (int o = 16; o; o >>= 1) { const int64_t t = __shfl_xor_sync(kFull, max_chunks, o); max_chunks = t > max_chunks ? t : max_chunks; }
-        // stage chunk c of the eight buffers: bytes [512 c, 512 c + 544) from abase, as far as they hold stripes
-        auto issue = [&](const int64_t c) {
+        for (int64_t c = 0; c < max_chunks; c++) {
+            // ---- stage chunk c of the eight buffers: bytes [512 c, 512 c + 544) from abase, as far as they hold stripes
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const uint8_t *ab = reinterpret_cast<const uint8_t *>(__shfl_sync(kFull, reinterpret_cast<uintptr_t>(abase), g * 4));
                 const int64_t nd = __shfl_sync(kFull, need, g * 4);
                 const int64_t o0 = c * kChunk + lane * 16;
-                if (o0 < nd) copy16_async(&stage[warp][c & 1][g][lane * 16], ab + o0);
+                if (o0 < nd) *reinterpret_cast<uint4 *>(&stage[warp][g][lane * 16]) = *reinterpret_cast<const uint4 *>(ab + o0);
                 const int64_t o1 = c * kChunk + kChunk + lane * 16;       // the 32 bytes behind the chunk: a misaligned last stripe ends there
-                if (lane < 2 && o1 < nd) copy16_async(&stage[warp][c & 1][g][kChunk + lane * 16], ab + o1);
+                if (lane < 2 && o1 < nd) *reinterpret_cast<uint4 *>(&stage[warp][g][kChunk + lane * 16]) = *reinterpret_cast<const uint4 *>(ab + o1);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        if (max_chunks) issue(0);
-        for (int64_t c = 0; c < max_chunks; c++) {
-            if (c + 1 < max_chunks) { issue(c + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             // ---- my group's stripes of this chunk
             if (c < my_chunks) {
                 const int n = (int) (stripes - (c << 5) < 32 ? stripes - (c << 5) : 32);
-                const uint8_t *row = &stage[warp][c & 1][grp][0];
+                const uint8_t *row = &stage[warp][grp][0];
                 const uint32_t off = k16 + (uint32_t) sub * 4, k = off & 3;
                 const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (off - k));
                 if (k == 0) {
