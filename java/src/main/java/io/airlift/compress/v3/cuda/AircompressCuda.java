@@ -55,6 +55,7 @@ final class AircompressCuda
     static final int OP_ZSTD_COMPRESS = 4;
     static final int OP_ZSTD_DECOMPRESS = 5;
     static final int OP_XXH64 = 6;
+    static final int OP_XXH32 = 7;
 
     private record MethodHandles(
             @NativeSignature(name = "acc_device_count", returnType = int.class, argumentTypes = {}) MethodHandle deviceCount,
@@ -78,6 +79,7 @@ final class AircompressCuda
             @NativeSignature(name = "acc_snappy_uncompressed_length", returnType = long.class, argumentTypes = {MemorySegment.class, long.class, MemorySegment.class}) MethodHandle snappyUncompressedLength,
             @NativeSignature(name = "acc_zstd_frame_content_size", returnType = long.class, argumentTypes = {MemorySegment.class, long.class, MemorySegment.class}) MethodHandle zstdFrameContentSize,
             @NativeSignature(name = "acc_xxh64", returnType = long.class, argumentTypes = {MemorySegment.class, MemorySegment.class, long.class, long.class}) MethodHandle xxh64,
+            @NativeSignature(name = "acc_xxh32", returnType = int.class, argumentTypes = {MemorySegment.class, MemorySegment.class, long.class, int.class}) MethodHandle xxh32,
             @NativeSignature(name = "acc_batch", returnType = int.class, argumentTypes = {MemorySegment.class, int.class,
                     MemorySegment.class, MemorySegment.class, MemorySegment.class, MemorySegment.class, MemorySegment.class, MemorySegment.class,
                     MemorySegment.class, MemorySegment.class, long.class, int.class, long.class}) MethodHandle batch) {}
@@ -193,6 +195,16 @@ final class AircompressCuda
     {
         try {
             return (long) H.xxh64().invokeExact(ctx, input, length, seed);
+        }
+        catch (Throwable e) {
+            throw new AssertionError("should not reach here", e);
+        }
+    }
+
+    static int xxh32(MemorySegment ctx, MemorySegment input, long length, int seed)
+    {
+        try {
+            return (int) H.xxh32().invokeExact(ctx, input, length, seed);
         }
         catch (Throwable e) {
             throw new AssertionError("should not reach here", e);
