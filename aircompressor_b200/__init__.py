@@ -1,5 +1,5 @@
 """aircompressor_b200 -- B200-native batched block-compression engine behind the
-io.airlift.compress.v3 Compressor/Decompressor API (LZ4, Snappy, Zstandard, XXH64; LZ4 frame format + XXH32).
+io.airlift.compress.v3 Compressor/Decompressor API (LZ4, Snappy, Zstandard, XXH64; LZ4 frame format + XXH32, Hadoop block streams).
 
 The product is aircompressor_b200/libaircompress_cuda.so (C ABI in include/aircompress_cuda.h);
 this package is the host-side mirror of the reference interface used by tests and bench.py.
@@ -11,3 +11,5 @@ from .api import (BatchEngine, Compressor, Decompressor, IllegalArgumentExceptio
                   MalformedInputException, SnappyCudaCompressor, SnappyCudaDecompressor, XxHash64CudaHasher,
                   ZstdCudaCompressor, ZstdCudaDecompressor)
 from .lz4_frame import Lz4FrameCudaCompressor, Lz4FrameCudaDecompressor, XxHash32CudaHasher
+from .hadoop_streams import (Lz4HadoopCudaInputStream, Lz4HadoopCudaOutputStream, SnappyHadoopCudaInputStream,
+                             SnappyHadoopCudaOutputStream)
