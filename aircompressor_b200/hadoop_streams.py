@@ -27,7 +27,6 @@ from . import _native as N
 from .api import BatchEngine, MalformedInputException
 
 DEFAULT_BUFFER_SIZE = 256 * 1024                 # Lz4HadoopStreams.java:29, SnappyHadoopStreams.java:29
-SIZE_OF_LONG = 8
 
 
 def lz4_overhead(size):
@@ -152,7 +151,6 @@ class _HadoopCudaInputStream(io.RawIOBase):
         super().__init__()
         self._engine = engine if engine is not None else BatchEngine(device)
         self._in = _Replay(inp)
-        self._buffer_size = buffer_size
         self._batch = max(1, batch_chunks)
         self._ready = bytearray()        # decoded, not yet delivered
         self._pending_error = None       # raised once `_ready` is drained

@@ -306,7 +306,6 @@ class Lz4FrameCudaDecompressor:
 
         # ---- pass 3: in the order of the Java loop -- place the blocks, report the first error it would have met
         out_pos = 0
-        bi = 0
         for fr in frames:
             frame_start = out_pos
             for i in range(fr.first_block, fr.first_block + fr.n_blocks):
@@ -336,7 +335,6 @@ class Lz4FrameCudaDecompressor:
                     expected = int.from_bytes(inp[b.checksum_pos:b.checksum_pos + 4].tobytes(), "little")
                     if expected != int(sums[i]):
                         raise MalformedInputException(b.checksum_pos, "Corrupt LZ4 frame: invalid block checksum")
-                bi += 1
             if fr.error is not None:
                 raise fr.error
             content_length = out_pos - frame_start
