@@ -189,3 +189,19 @@ def test_frame_host_logic_reports_in_the_order_of_the_java_loop(oracle, pieces):
         n = dec.decompress(frame, 0, len(frame), out, 0, cap)
         assert n == len(want) and out[:n].tobytes() == want and (out[cap:] == 0xA5).all(), i
     assert n_bad > 40
+
+
+def test_frame_host_logic_splits_large_calls_into_several_batches(oracle, pieces):
+    """A call whose blocks need more scratch than the per-batch budget is decoded in several batches (host logic, mock engine)."""
+    from aircompressor_b200.lz4_frame import Lz4FrameCudaDecompressor
+    dec = object.__new__(Lz4FrameCudaDecompressor)
+    dec._engine, dec._x = _MockEngine(oracle), _MockXxh32(oracle)
+    dec.BLOCKS_PER_BATCH_BYTES = 200000                                  # three 64 KiB slots per batch
+    blob = (CONTENT * 3 + bytes(range(256))) * 1800                       # 693,000 compressible bytes
+    frame = Lz4fNative().compress(blob, 4, True, True, True)              # eleven 64 KiB blocks, block + content checksums
+    calls = []
+    run = dec._engine.run_host
+    dec._engine.run_host = lambda *a: (calls.append(len(a[2])), run(*a))[1]
+    out = np.zeros(len(blob), dtype=np.uint8)
+    assert dec.decompress(frame, 0, len(frame), out, 0, len(out)) == len(blob) and out.tobytes() == blob
+    assert len(calls) >= 3 and sum(calls) == 11
