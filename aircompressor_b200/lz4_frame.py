@@ -160,7 +160,7 @@ class _Block:
 
 
 class _Frame:
-    __slots__ = ("first_block", "n_blocks", "content_checksum_pos", "expected_content_size", "end_pos", "error")
+    __slots__ = ("first_block", "n_blocks", "content_checksum_pos", "has_content_size", "expected_content_size", "end_pos", "error")
 
 
 class Lz4FrameCudaDecompressor:
@@ -191,7 +191,7 @@ class Lz4FrameCudaDecompressor:
             if magic == MAGIC:
                 fr = _Frame()
                 fr.first_block, fr.n_blocks, fr.error = len(blocks), 0, None
-                fr.content_checksum_pos, fr.expected_content_size, fr.end_pos = -1, -1, -1
+                fr.content_checksum_pos, fr.expected_content_size, fr.end_pos, fr.has_content_size = -1, -1, -1, False
                 frames.append(fr)
                 d0 = pos + 4
                 if d0 + 2 > n_in:
@@ -214,6 +214,7 @@ class Lz4FrameCudaDecompressor:
                 if p + (8 if has_size else 0) + 1 > n_in:
                     error = fail(p, "Truncated LZ4 frame header"); break
                 if has_size:
+                    fr.has_content_size = True
                     fr.expected_content_size = int.from_bytes(inp[p:p + 8].tobytes(), "little", signed=True)
                     p += 8
                 if int(inp[p]) != (self._x.hash(inp, d0, p - d0) >> 8) & 0xFF:
@@ -342,7 +343,7 @@ class Lz4FrameCudaDecompressor:
                 expected = int.from_bytes(inp[fr.content_checksum_pos:fr.content_checksum_pos + 4].tobytes(), "little")
                 if expected != self._x.hash(out, frame_start, content_length):
                     raise MalformedInputException(fr.content_checksum_pos, "Corrupt LZ4 frame: invalid content checksum")
-            if fr.expected_content_size != -1 and content_length != fr.expected_content_size:
+            if fr.has_content_size and content_length != fr.expected_content_size:
                 raise MalformedInputException(fr.end_pos, "Corrupt LZ4 frame: content size does not match frame header")
         if walk_error is not None:
             raise walk_error
